@@ -1,0 +1,50 @@
+// BICOS::match -- the reference's one public entry point (reference include/match.hpp:31-41,
+// src/lib.cpp:31-49), implemented on hand-written sm_100a kernels through the C ABI in
+// include/bicos_b200.h.
+//
+//  * stack0 / stack1: n >= 2 rectified single-channel device images per side, all of one
+//    size and depth (8U or 16U). Borrowed, never modified.
+//  * disparity: (re)allocated by the callee. int16 (-32768 = invalid) when
+//    cfg.nxcorr_threshold is unset; float32 otherwise: integer mode keeps -32768.0f as the
+//    invalid marker, subpixel mode uses NaN -- the reference CPU backend's convention
+//    (src/impl/cpu.cpp:77-95), which is the parity oracle of this implementation.
+//  * corrmap: only touched when cfg.nxcorr_threshold is set; float32 (SINGLE) or float64
+//    (DOUBLE), NaN where no correlation was evaluated.
+//  * stream: a cudaStream_t (nullptr = default stream). Work is enqueued, not synchronised.
+//
+// Errors: BICOS::Exception for n < 2, bad depths and CUDA failures; std::invalid_argument
+// when the stack needs more than 256 descriptor bits -- as in the reference
+// (src/impl/cpu.cpp:110-114,154-155; include/impl/cuda/cutil.cuh:32-41). Deviations:
+// mismatching image sizes/types inside a stack throw (undefined behaviour in the reference),
+// and a negative nxcorr_threshold means "unset" as it does in the reference's own C ABI.
+#pragma once
+
+#include "common.hpp"
+
+#include <vector>
+
+namespace BICOS {
+
+void match(
+    const std::vector<Image>& stack0,
+    const std::vector<Image>& stack1,
+    Image& disparity,
+    Config cfg = Config {},
+    Image* corrmap = nullptr,
+    void* stream = nullptr
+);
+
+// Row-sharded match over several GPUs of one node from a single process: device g handles
+// rows [g*H/G, (g+1)*H/G) and writes its rows of `disparity` / `corrmap` (allocated on
+// devices[0]) over NVLink peer access. Inputs must be resident on devices[0] and peer
+// access between devices[0] and the others must be available.
+void match_sharded(
+    const std::vector<Image>& stack0,
+    const std::vector<Image>& stack1,
+    Image& disparity,
+    const std::vector<int>& devices,
+    Config cfg = Config {},
+    Image* corrmap = nullptr
+);
+
+} // namespace BICOS

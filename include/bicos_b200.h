@@ -1,0 +1,150 @@
+/* bicos_b200.h -- thin C ABI over the sm_100a kernels of the BICOS::match hot path.
+ *
+ * This is the drop-in boundary underneath the reference's public entry point
+ *     void BICOS::match(const std::vector<Image>&, const std::vector<Image>&,
+ *                       Image& disparity, Config, Image* corrmap [, Stream&])
+ *     (reference include/match.hpp:31-41, defined src/lib.cpp:31-49)
+ * and underneath its Python FFI (reference src/pybicos_c.cpp:92-209, declared for this
+ * repository in include/pybicos_c.h). A maintainer of the reference would replace the body
+ * of impl::cuda::match (reference src/impl/cuda.cu:465-524) by one call to
+ * bicos_b200_match(); INTEGRATION.md shows that stub.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * negative bicos_b200_status and records a message retrievable with
+ * bicos_b200_last_error() (thread-local). No exceptions cross this boundary. All device
+ * pointers must belong to the device the handle was created on. Work is enqueued on the
+ * given stream (a cudaStream_t passed as void*; NULL = the legacy default stream) and is
+ * NOT synchronised unless stated. There is no CPU fallback: without a CUDA device every
+ * compute entry point fails with BICOS_B200_ERR_CUDA.
+ */
+#ifndef BICOS_B200_H
+#define BICOS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BICOS_B200_MAX_IMAGES 65 /* 4n-6 <= 256 descriptor bits; reference src/impl/cuda.cu:107 */
+
+typedef enum {
+    BICOS_B200_OK = 0,
+    BICOS_B200_ERR_INVALID = -1, /* BICOS::Exception / std::invalid_argument in the reference */
+    BICOS_B200_ERR_CUDA = -2, /* assertCudaSuccess, reference include/impl/cuda/cutil.cuh:32-41 */
+    BICOS_B200_ERR_NOMEM = -3
+} bicos_b200_status;
+
+/* OpenCV depth codes, as the reference's C ABI passes them (pybicos/__init__.py:79-83) */
+#define BICOS_B200_8U 0
+#define BICOS_B200_16U 2
+#define BICOS_B200_16S 3
+#define BICOS_B200_32F 5
+#define BICOS_B200_64F 6
+
+/* reference include/impl/common.hpp:46-47 */
+#define BICOS_B200_FLAG_NODUPES 1
+#define BICOS_B200_FLAG_CONSISTENCY 2
+
+/* Same fields, order and "negative float = unset" convention as the reference's BicosConfig
+ * (src/pybicos_c.cpp:30-41 with BICOS_CUDA defined; pybicos/__init__.py:41-51). */
+typedef struct {
+    float nxcorr_threshold; /* < 0: no NXC stage, int16 result (Config::nxcorr_threshold = nullopt) */
+    float subpixel_step; /* < 0: integer disparities */
+    float min_variance; /* < 0: no variance test */
+    int mode; /* 0 = TransformMode::LIMITED, 1 = FULL */
+    int precision; /* 0 = Precision::SINGLE, 1 = DOUBLE */
+    int variant_type; /* 0 = Variant::NoDuplicates, 1 = Variant::Consistency */
+    int max_lr_diff; /* Consistency only */
+    int no_dupes; /* Consistency only */
+} bicos_b200_config;
+
+typedef struct bicos_b200_handle_s* bicos_b200_handle;
+
+const char* bicos_b200_last_error(void);
+
+/* Number of CUDA devices visible, or a negative status. */
+int bicos_b200_device_count(void);
+
+/* A handle owns the per-device workspace (descriptor buffers, search keys, the subpixel x
+ * table, pinned staging for the *_host entry point). One handle serves one match at a time;
+ * use one handle per concurrent stream. device < 0 = current device. */
+int bicos_b200_create(bicos_b200_handle* out, int device);
+int bicos_b200_destroy(bicos_b200_handle h);
+
+/* Words (uint32) per descriptor the reference's dispatch picks for n images
+ * (src/impl/cpu.cpp:122-156): 1/2/4/8, or BICOS_B200_ERR_INVALID above 256 bits. */
+int bicos_b200_descriptor_words(int n, int mode);
+
+/* Result type codes for a configuration: disparity BICOS_B200_16S (no threshold) or
+ * BICOS_B200_32F; corrmap BICOS_B200_32F / BICOS_B200_64F, 0 when no threshold is set. */
+int bicos_b200_disparity_type(const bicos_b200_config* cfg);
+int bicos_b200_corrmap_type(const bicos_b200_config* cfg);
+
+/* ---- the path, stage by stage (device memory) --------------------------------------- */
+
+/* Stage 1, reference descriptor_transform<>() (include/impl/cpu/descriptor_transform.hpp:125-138).
+ * planes: host array of n device pointers to single-channel images [rows][pitch_bytes].
+ * desc: device [rows][desc_pitch_words] uint32, K words per pixel, rows 16-byte aligned. */
+int bicos_b200_transform(bicos_b200_handle h, const void* const* planes, int n, int rows, int cols,
+                         size_t pitch_bytes, int depth, int mode, uint32_t* desc,
+                         size_t desc_pitch_words, void* stream);
+
+/* Stage 2+4a, reference bicos<>() search part (include/impl/cpu/bicos.hpp:50-76, 78-97).
+ * fwd_best: device [rows][cols] int32 (best right column, -1 = no unique match).
+ * rev_first / rev_last: device [rows][cols] uint32 column minima, needed for
+ * FLAG_CONSISTENCY (rev_last only with FLAG_NODUPES as well); filled by this call. */
+int bicos_b200_search(bicos_b200_handle h, const uint32_t* desc0, const uint32_t* desc1, int K,
+                      int rows, int cols, size_t desc_pitch_words, int flags, int32_t* fwd_best,
+                      uint32_t* rev_first, uint32_t* rev_last, void* stream);
+
+/* Stage 4b+3, reference bicos<>() postfilter (bicos.hpp:95-110) + agree / agree_subpixel
+ * (include/impl/cpu/agree.hpp:53-191). raw_disp_out (optional, dense int16 [rows][cols])
+ * receives the postfilter result before the NXC test. */
+int bicos_b200_refine(bicos_b200_handle h, const void* const* planes0, const void* const* planes1,
+                      int n, int rows, int cols, size_t pitch_bytes, int depth,
+                      const bicos_b200_config* cfg, const int32_t* fwd_best,
+                      const uint32_t* rev_first, const uint32_t* rev_last, int16_t* raw_disp_out,
+                      void* disparity, size_t disparity_pitch_bytes, void* corrmap,
+                      size_t corrmap_pitch_bytes, void* stream);
+
+/* ---- the whole path ------------------------------------------------------------------ */
+
+/* Device-resident BICOS::match: transform x2 -> search -> postfilter+refine on `stream`.
+ * disparity: int16 (no threshold) or float32 rows of disparity_pitch_bytes; integer mode with a
+ * threshold keeps -32768.0f as the invalid marker, subpixel mode uses NaN (reference CPU
+ * backend, src/impl/cpu.cpp:77-95). corrmap may be NULL; otherwise float32 (SINGLE) or
+ * float64 (DOUBLE), NaN where no correlation was evaluated. */
+int bicos_b200_match(bicos_b200_handle h, const void* const* planes0, const void* const* planes1,
+                     int n, int rows, int cols, size_t pitch_bytes, int depth,
+                     const bicos_b200_config* cfg, void* disparity, size_t disparity_pitch_bytes,
+                     void* corrmap, size_t corrmap_pitch_bytes, void* stream);
+
+/* Host-resident variant (what pybicos' BICOS_Match needs): dense host images in, dense host
+ * results out; uploads, runs bicos_b200_match and downloads through the handle's pinned
+ * staging buffers, then synchronises. */
+int bicos_b200_match_host(bicos_b200_handle h, const void* const* host_planes0,
+                          const void* const* host_planes1, int n, int rows, int cols, int depth,
+                          const bicos_b200_config* cfg, void* host_disparity, void* host_corrmap);
+
+/* Row-sharded variant for one process driving several GPUs: rows [row_begin, row_end) of the
+ * same device-resident inputs are matched on this handle's device and written into the
+ * matching rows of the (possibly peer-mapped) output buffers. Rows are independent
+ * (SURVEY.md 8e), so no halo and no collective is involved. */
+int bicos_b200_match_rows(bicos_b200_handle h, const void* const* planes0,
+                          const void* const* planes1, int n, int rows, int cols, size_t pitch_bytes,
+                          int depth, const bicos_b200_config* cfg, int row_begin, int row_end,
+                          void* disparity, size_t disparity_pitch_bytes, void* corrmap,
+                          size_t corrmap_pitch_bytes, void* stream);
+
+/* Blocks until all work enqueued through this handle's internal streams and `stream` is done. */
+int bicos_b200_synchronize(bicos_b200_handle h, void* stream);
+
+/* How many kernels of this library have been launched through the handle (bench bookkeeping). */
+long long bicos_b200_kernel_launches(bicos_b200_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BICOS_B200_H */

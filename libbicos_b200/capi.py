@@ -1,0 +1,297 @@
+"""ctypes binding of include/bicos_b200.h for callers that hold device memory in torch tensors.
+
+PyTorch is plumbing here (allocation, streams, torch.distributed); every computation on the
+path happens inside libbicos_b200.so. There is no fallback: if the shared library is missing
+or no CUDA device is present, the calls raise.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libbicos_b200.so")
+
+DEPTH_8U, DEPTH_16U, TYPE_16S, TYPE_32F, TYPE_64F = 0, 2, 3, 5, 6
+FLAG_NODUPES, FLAG_CONSISTENCY = 1, 2
+MAX_IMAGES = 65
+
+EXPORTS = (
+    "bicos_b200_last_error", "bicos_b200_device_count", "bicos_b200_create", "bicos_b200_destroy",
+    "bicos_b200_descriptor_words", "bicos_b200_disparity_type", "bicos_b200_corrmap_type",
+    "bicos_b200_transform", "bicos_b200_search", "bicos_b200_refine", "bicos_b200_match",
+    "bicos_b200_match_host", "bicos_b200_match_rows", "bicos_b200_synchronize",
+    "bicos_b200_kernel_launches",
+)
+
+
+class BicosError(RuntimeError):
+    """Raised for every non-zero status of the C ABI (BICOS::Exception in the reference)."""
+
+
+class CConfig(ctypes.Structure):
+    """bicos_b200_config == the reference's BicosConfig (src/pybicos_c.cpp:30-41)."""
+
+    _fields_ = [
+        ("nxcorr_threshold", ctypes.c_float),
+        ("subpixel_step", ctypes.c_float),
+        ("min_variance", ctypes.c_float),
+        ("mode", ctypes.c_int),
+        ("precision", ctypes.c_int),
+        ("variant_type", ctypes.c_int),
+        ("max_lr_diff", ctypes.c_int),
+        ("no_dupes", ctypes.c_int),
+    ]
+
+
+@dataclass
+class Config:
+    """Python mirror of BICOS::Config (reference include/common.hpp:73-82)."""
+
+    nxcorr_threshold: Optional[float] = 0.5
+    subpixel_step: Optional[float] = None
+    min_variance: Optional[float] = None
+    mode_full: bool = False  # TransformMode::FULL
+    double: bool = False  # Precision::DOUBLE
+    consistency: bool = False  # Variant::Consistency instead of Variant::NoDuplicates
+    max_lr_diff: int = 1
+    no_dupes: bool = False
+
+    def to_c(self) -> CConfig:
+        def opt(v):
+            return -1.0 if v is None else float(v)
+
+        return CConfig(opt(self.nxcorr_threshold), opt(self.subpixel_step), opt(self.min_variance),
+                       int(self.mode_full), int(self.double), int(self.consistency),
+                       int(self.max_lr_diff), int(self.no_dupes))
+
+    @property
+    def flags(self) -> int:
+        if self.consistency:
+            return FLAG_CONSISTENCY | (FLAG_NODUPES if self.no_dupes else 0)
+        return FLAG_NODUPES
+
+
+_lib = None
+
+
+def lib():
+    """The loaded libbicos_b200.so. Raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BicosError(
+                f"{LIB_PATH} is missing: build it with `make -C libbicos_b200/csrc` "
+                "(or __graft_entry__.build()); there is no CPU or PyTorch fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        L.bicos_b200_last_error.restype = ctypes.c_char_p
+        L.bicos_b200_kernel_launches.restype = ctypes.c_longlong
+        L.bicos_b200_kernel_launches.argtypes = [ctypes.c_void_p]
+        vp, i, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+        cfgp = ctypes.POINTER(CConfig)
+        pp = ctypes.POINTER(ctypes.c_void_p)
+        L.bicos_b200_create.argtypes = [ctypes.POINTER(vp), i]
+        L.bicos_b200_destroy.argtypes = [vp]
+        L.bicos_b200_descriptor_words.argtypes = [i, i]
+        L.bicos_b200_disparity_type.argtypes = [cfgp]
+        L.bicos_b200_corrmap_type.argtypes = [cfgp]
+        L.bicos_b200_transform.argtypes = [vp, pp, i, i, i, sz, i, i, vp, sz, vp]
+        L.bicos_b200_search.argtypes = [vp, vp, vp, i, i, i, sz, i, vp, vp, vp, vp]
+        L.bicos_b200_refine.argtypes = [vp, pp, pp, i, i, i, sz, i, cfgp, vp, vp, vp, vp, vp, sz, vp, sz, vp]
+        L.bicos_b200_match.argtypes = [vp, pp, pp, i, i, i, sz, i, cfgp, vp, sz, vp, sz, vp]
+        L.bicos_b200_match_rows.argtypes = [vp, pp, pp, i, i, i, sz, i, cfgp, i, i, vp, sz, vp, sz, vp]
+        L.bicos_b200_match_host.argtypes = [vp, pp, pp, i, i, i, i, cfgp, vp, vp]
+        L.bicos_b200_synchronize.argtypes = [vp, vp]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> int:
+    if rc < 0:
+        raise BicosError(lib().bicos_b200_last_error().decode())
+    return rc
+
+
+def descriptor_words(n: int, mode_full: bool = False) -> int:
+    return _check(lib().bicos_b200_descriptor_words(n, int(mode_full)))
+
+
+def _ptr_array(ptrs: Sequence[int]):
+    arr = (ctypes.c_void_p * len(ptrs))()
+    for k, p in enumerate(ptrs):
+        arr[k] = p
+    return arr
+
+
+class Handle:
+    """Owns one per-device workspace (bicos_b200_handle)."""
+
+    def __init__(self, device: Optional[int] = None):
+        h = ctypes.c_void_p()
+        _check(lib().bicos_b200_create(ctypes.byref(h), -1 if device is None else int(device)))
+        self._h = h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().bicos_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(lib().bicos_b200_kernel_launches(self._h))
+
+    # ---- torch-tensor helpers -----------------------------------------------------------
+    @staticmethod
+    def _stack_info(stack):
+        import torch
+
+        if stack.dim() != 3 or not stack.is_cuda:
+            raise BicosError("stacks must be CUDA tensors of shape [n, rows, cols]")
+        if stack.dtype == torch.uint8:
+            depth, eb = DEPTH_8U, 1
+        elif stack.dtype == torch.uint16:
+            depth, eb = DEPTH_16U, 2
+        else:
+            raise BicosError("bad input depths, only uint8 and uint16 are supported")
+        if stack.stride(2) != 1:
+            raise BicosError("stack rows must be contiguous")
+        n, rows, cols = stack.shape
+        pitch = stack.stride(1) * eb
+        planes = _ptr_array([stack.data_ptr() + stack.stride(0) * eb * t for t in range(n)])
+        return planes, n, rows, cols, pitch, depth
+
+    @staticmethod
+    def _stream():
+        import torch
+
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    # ---- stages -------------------------------------------------------------------------
+    def transform(self, stack, mode_full: bool = False):
+        """Descriptor transform of one stack -> int32 tensor [rows, cols, K] (a view of pitched rows)."""
+        import torch
+
+        planes, n, rows, cols, pitch, depth = self._stack_info(stack)
+        k = descriptor_words(n, mode_full)
+        pitch_words = (cols * k + 3) // 4 * 4
+        desc = torch.empty((rows, pitch_words), dtype=torch.int32, device=stack.device)
+        _check(lib().bicos_b200_transform(self._h, planes, n, rows, cols, pitch, depth, int(mode_full),
+                                          desc.data_ptr(), pitch_words, self._stream()))
+        return desc, k
+
+    def search(self, desc0, desc1, k: int, cols: int, flags: int):
+        """Row-wise search on pitched descriptors -> (fwd_best, rev_first, rev_last) [rows, cols]."""
+        import torch
+
+        rows, pitch_words = desc0.shape
+        dev = desc0.device
+        fwd = torch.empty((rows, cols), dtype=torch.int32, device=dev)
+        revf = torch.empty((rows, cols), dtype=torch.int32, device=dev) if flags & FLAG_CONSISTENCY else None
+        revl = torch.empty((rows, cols), dtype=torch.int32, device=dev) if flags == 3 else None
+        _check(lib().bicos_b200_search(self._h, desc0.data_ptr(), desc1.data_ptr(), k, rows, cols, pitch_words,
+                                       flags, fwd.data_ptr(), revf.data_ptr() if revf is not None else None,
+                                       revl.data_ptr() if revl is not None else None, self._stream()))
+        return fwd, revf, revl
+
+    def _outputs(self, cfg: Config, rows: int, cols: int, device):
+        import torch
+
+        ccfg = cfg.to_c()
+        dt = lib().bicos_b200_disparity_type(ctypes.byref(ccfg))
+        ct = lib().bicos_b200_corrmap_type(ctypes.byref(ccfg))
+        disp = torch.empty((rows, cols), dtype=torch.int16 if dt == TYPE_16S else torch.float32, device=device)
+        corr = None
+        if ct:
+            corr = torch.empty((rows, cols), dtype=torch.float64 if ct == TYPE_64F else torch.float32, device=device)
+        return ccfg, disp, corr
+
+    def refine(self, stack0, stack1, cfg: Config, fwd, revf=None, revl=None, want_raw: bool = True):
+        """Postfilter + NXC refinement -> (disparity, corrmap or None, raw int16 or None)."""
+        import torch
+
+        p0, n, rows, cols, pitch, depth = self._stack_info(stack0)
+        p1, n1, rows1, cols1, pitch1, depth1 = self._stack_info(stack1)
+        if (n1, rows1, cols1, pitch1, depth1) != (n, rows, cols, pitch, depth):
+            raise BicosError("stack0 and stack1 differ")
+        ccfg, disp, corr = self._outputs(cfg, rows, cols, stack0.device)
+        raw = torch.empty((rows, cols), dtype=torch.int16, device=stack0.device) if want_raw else None
+        _check(lib().bicos_b200_refine(
+            self._h, p0, p1, n, rows, cols, pitch, depth, ctypes.byref(ccfg), fwd.data_ptr(),
+            revf.data_ptr() if revf is not None else None, revl.data_ptr() if revl is not None else None,
+            raw.data_ptr() if raw is not None else None, disp.data_ptr(), disp.stride(0) * disp.element_size(),
+            corr.data_ptr() if corr is not None else None,
+            corr.stride(0) * corr.element_size() if corr is not None else 0, self._stream()))
+        return disp, corr, raw
+
+    # ---- whole path ---------------------------------------------------------------------
+    def match(self, stack0, stack1, cfg: Config, out=None, rows_range=None):
+        """Device-resident BICOS::match on [n, rows, cols] uint8/uint16 CUDA tensors.
+
+        ``out`` = (disparity, corrmap) tensors to reuse; ``rows_range`` = (begin, end) matches only
+        those rows (row-sharding) and leaves the others of ``out`` untouched.
+        """
+        p0, n, rows, cols, pitch, depth = self._stack_info(stack0)
+        p1, n1, rows1, cols1, pitch1, depth1 = self._stack_info(stack1)
+        if (n1, rows1, cols1, pitch1, depth1) != (n, rows, cols, pitch, depth):
+            raise BicosError("stack0 and stack1 differ")
+        if out is None:
+            ccfg, disp, corr = self._outputs(cfg, rows, cols, stack0.device)
+        else:
+            ccfg = cfg.to_c()
+            disp, corr = out
+        args = [disp.data_ptr(), disp.stride(0) * disp.element_size(),
+                corr.data_ptr() if corr is not None else None,
+                corr.stride(0) * corr.element_size() if corr is not None else 0, self._stream()]
+        if rows_range is None:
+            _check(lib().bicos_b200_match(self._h, p0, p1, n, rows, cols, pitch, depth, ctypes.byref(ccfg), *args))
+        else:
+            _check(lib().bicos_b200_match_rows(self._h, p0, p1, n, rows, cols, pitch, depth, ctypes.byref(ccfg),
+                                               int(rows_range[0]), int(rows_range[1]), *args))
+        return disp, corr
+
+    def match_host(self, stack0, stack1, cfg: Config, out=None):
+        """Host-resident match on numpy arrays / CPU tensors [n, rows, cols]; H2D and D2H included."""
+        import numpy as np
+
+        def as_np(a):
+            if hasattr(a, "numpy") and not isinstance(a, np.ndarray):
+                a = a.numpy()
+            return a
+
+        s0, s1 = as_np(stack0), as_np(stack1)
+        if s0.shape != s1.shape or s0.dtype != s1.dtype or s0.ndim != 3:
+            raise BicosError("stack0 and stack1 differ")
+        if s0.dtype == np.uint8:
+            depth = DEPTH_8U
+        elif s0.dtype == np.uint16:
+            depth = DEPTH_16U
+        else:
+            raise BicosError("bad input depths, only uint8 and uint16 are supported")
+        n, rows, cols = s0.shape
+        planes0 = [np.ascontiguousarray(s0[t]) for t in range(n)]
+        planes1 = [np.ascontiguousarray(s1[t]) for t in range(n)]
+        ccfg = cfg.to_c()
+        dt = lib().bicos_b200_disparity_type(ctypes.byref(ccfg))
+        ct = lib().bicos_b200_corrmap_type(ctypes.byref(ccfg))
+        if out is None:
+            disp = np.empty((rows, cols), dtype=np.int16 if dt == TYPE_16S else np.float32)
+            corr = np.empty((rows, cols), dtype=np.float64 if ct == TYPE_64F else np.float32) if ct else None
+        else:
+            disp, corr = (as_np(o) if o is not None else None for o in out)
+        _check(lib().bicos_b200_match_host(
+            self._h, _ptr_array([p.ctypes.data for p in planes0]), _ptr_array([p.ctypes.data for p in planes1]),
+            n, rows, cols, depth, ctypes.byref(ccfg), disp.ctypes.data,
+            corr.ctypes.data if corr is not None else None))
+        return disp, corr
+
+    def synchronize(self) -> None:
+        _check(lib().bicos_b200_synchronize(self._h, self._stream()))

@@ -1,0 +1,537 @@
+// C-ABI layer (include/bicos_b200.h) over the three kernels: argument validation with the
+// reference's error behaviour, the per-device workspace, stage sequencing, and the
+// host-buffer variant that pybicos' BICOS_Match builds on.
+//
+// Reference behaviour mirrored here (not its structure):
+//   src/impl/cpu.cpp:100-159 / src/impl/cuda.cu:465-524   validation + descriptor width choice
+//   src/impl/cpu.cpp:35-98                                 stage order and output types
+//   src/pybicos_c.cpp:56-89                                negative float = unset optional
+
+#include "../../include/bicos_b200.h"
+#include "kernels.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace bicos_b200;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+int cuda_fail(cudaError_t err, const char* what) {
+    return fail(BICOS_B200_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(err), cudaGetErrorName(err));
+}
+
+#define CU(call) \
+    do { \
+        cudaError_t err__ = (call); \
+        if (err__ != cudaSuccess) \
+            return cuda_fail(err__, #call); \
+    } while (0)
+
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t cap = 0;
+
+    // grow-only; a reallocation waits for the device so no kernel still reads the old block
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap)
+            return cudaSuccess;
+        cudaError_t err = cudaDeviceSynchronize();
+        if (err != cudaSuccess)
+            return err;
+        if (ptr)
+            cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        err = cudaMalloc(&ptr, bytes);
+        if (err == cudaSuccess)
+            cap = bytes;
+        return err;
+    }
+    void release() {
+        if (ptr)
+            cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess)
+            ok = false;
+        else if (prev != device && cudaSetDevice(device) != cudaSuccess)
+            ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0)
+            cudaSetDevice(prev);
+    }
+};
+
+int descriptor_bits(int n, int mode) {
+    // src/impl/cpu.cpp:122-124 (LIMITED is undercounted by one there; no bucket boundary moves)
+    return mode ? n * n - 2 * n + 3 : 4 * n - 7;
+}
+
+int words_for_bits(int bits) {
+    if (bits <= 32)
+        return 1;
+    if (bits <= 64)
+        return 2;
+    if (bits <= 128)
+        return 4;
+    if (bits <= 256)
+        return 8;
+    return -1;
+}
+
+size_t depth_bytes(int depth) {
+    return depth == BICOS_B200_16U ? 2 : 1;
+}
+
+} // namespace
+
+struct bicos_b200_handle_s {
+    int device = 0;
+    DeviceBuffer desc0, desc1, fwd, rev_first, rev_last, xs;
+    DeviceBuffer stage_in, stage_disp, stage_corr;
+    float xs_step = -1.f;
+    int xs_count = 0;
+    long long launches = 0;
+};
+
+namespace {
+
+int validate_common(int n, int rows, int cols, int depth, const bicos_b200_config* cfg, int* K_out) {
+    if (!cfg)
+        return fail(BICOS_B200_ERR_INVALID, "config is null");
+    if (n < 2)
+        return fail(BICOS_B200_ERR_INVALID, "need at least two images"); // cpu.cpp:110-111
+    if (depth != BICOS_B200_8U && depth != BICOS_B200_16U)
+        return fail(BICOS_B200_ERR_INVALID, "bad input depths, only CV_8UC1 and CV_16UC1 are supported"); // cpu.cpp:113-114
+    const int bits = descriptor_bits(n, cfg->mode != 0);
+    const int K = words_for_bits(bits);
+    if (K < 0 || n > MAX_IMAGES)
+        return fail(BICOS_B200_ERR_INVALID, "input stacks too large, would require %d bits", bits); // cpu.cpp:154-155
+    if (rows <= 0 || cols <= 0)
+        return fail(BICOS_B200_ERR_INVALID, "empty images");
+    if (cols > 32767 || rows > 65535)
+        return fail(BICOS_B200_ERR_INVALID, "image too large: at most 32767 columns (int16 disparity) and 65535 rows");
+    if (cfg->nxcorr_threshold >= 0 && cfg->subpixel_step == 0.0f)
+        return fail(BICOS_B200_ERR_INVALID, "subpixel_step must be positive (the reference loops forever on 0)");
+    if (K_out)
+        *K_out = K;
+    return 0;
+}
+
+int search_flags(const bicos_b200_config* cfg) {
+    // src/impl/cpu.cpp:68-75
+    if (cfg->variant_type != 0)
+        return FLAG_CONSISTENCY | (cfg->no_dupes ? FLAG_NODUPES : 0);
+    return FLAG_NODUPES;
+}
+
+int fill_table(PlaneTable& t, const void* const* planes, int n, size_t row_offset_bytes) {
+    for (int i = 0; i < n; ++i) {
+        if (!planes[i])
+            return fail(BICOS_B200_ERR_INVALID, "image %d is null", i);
+        t.p[i] = static_cast<const char*>(planes[i]) + row_offset_bytes;
+    }
+    for (int i = n; i < MAX_IMAGES; ++i)
+        t.p[i] = nullptr;
+    return 0;
+}
+
+// the x values of `for (float x = -1.f; x <= 1.f; x += step)` (agree.hpp:165), cached per step
+int prepare_steps(bicos_b200_handle h, float step, cudaStream_t stream) {
+    if (h->xs_count > 0 && h->xs_step == step)
+        return 0;
+    std::vector<float> xs;
+    for (float x = -1.f; x <= 1.f; x += step) {
+        xs.push_back(x);
+        if (xs.size() > (1u << 16))
+            return fail(BICOS_B200_ERR_INVALID, "subpixel_step %g too small (more than 65536 steps)", (double)step);
+    }
+    CU(h->xs.reserve(xs.size() * sizeof(float)));
+    CU(cudaMemcpyAsync(h->xs.ptr, xs.data(), xs.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    CU(cudaStreamSynchronize(stream)); // xs is a stack-owned pageable buffer
+    h->xs_step = step;
+    h->xs_count = (int)xs.size();
+    return 0;
+}
+
+size_t desc_pitch_for(int cols, int K) {
+    return ((size_t)cols * K + 3) & ~(size_t)3; // rows start 16 B aligned
+}
+
+int do_refine(
+    bicos_b200_handle h,
+    const PlaneTable& t0,
+    const PlaneTable& t1,
+    int n,
+    int rows,
+    int cols,
+    size_t pitch_bytes,
+    int depth,
+    const bicos_b200_config* cfg,
+    const int32_t* fwd_best,
+    const uint32_t* rev_first,
+    const uint32_t* rev_last,
+    int16_t* raw_out,
+    void* disparity,
+    size_t disparity_pitch,
+    void* corrmap,
+    size_t corrmap_pitch,
+    cudaStream_t stream
+) {
+    RefineParams prm {};
+    prm.n = n;
+    prm.rows = rows;
+    prm.cols = cols;
+    prm.in_pitch = pitch_bytes;
+    prm.is_u16 = depth == BICOS_B200_16U;
+    prm.is_double = cfg->precision != 0;
+    prm.consistency = cfg->variant_type != 0;
+    prm.nodupes_reverse = prm.consistency && cfg->no_dupes;
+    prm.max_lr_diff = cfg->max_lr_diff;
+    prm.has_threshold = cfg->nxcorr_threshold >= 0;
+    prm.threshold = cfg->nxcorr_threshold;
+    prm.has_minvar = cfg->min_variance >= 0;
+    prm.minvar_times_n = prm.has_minvar ? cfg->min_variance * (float)n : 0.f; // cpu.cpp:127
+    prm.subpixel = prm.has_threshold && cfg->subpixel_step >= 0;
+    prm.nsteps = 0;
+    prm.xs = nullptr;
+    if (prm.subpixel) {
+        if (int rc = prepare_steps(h, cfg->subpixel_step, stream))
+            return rc;
+        prm.nsteps = h->xs_count;
+        prm.xs = static_cast<const float*>(h->xs.ptr);
+    }
+    prm.fwd_best = fwd_best;
+    prm.rev_first = rev_first;
+    prm.rev_last = rev_last;
+    prm.raw_out = raw_out;
+    prm.disp_out = disparity;
+    prm.disp_pitch = disparity_pitch;
+    prm.corr_out = prm.has_threshold ? corrmap : nullptr;
+    prm.corr_pitch = corrmap_pitch;
+    CU(launch_refine(t0, t1, prm, stream));
+    h->launches += 1;
+    return 0;
+}
+
+int do_match(
+    bicos_b200_handle h,
+    const void* const* planes0,
+    const void* const* planes1,
+    int n,
+    int rows,
+    int cols,
+    size_t pitch_bytes,
+    int depth,
+    const bicos_b200_config* cfg,
+    int row_begin,
+    int row_end,
+    void* disparity,
+    size_t disparity_pitch,
+    void* corrmap,
+    size_t corrmap_pitch,
+    cudaStream_t stream
+) {
+    int K = 0;
+    if (int rc = validate_common(n, rows, cols, depth, cfg, &K))
+        return rc;
+    if (!planes0 || !planes1 || !disparity)
+        return fail(BICOS_B200_ERR_INVALID, "null argument");
+    if (row_begin < 0 || row_end > rows || row_begin >= row_end)
+        return fail(BICOS_B200_ERR_INVALID, "bad row range [%d, %d) of %d", row_begin, row_end, rows);
+    if (pitch_bytes < (size_t)cols * depth_bytes(depth))
+        return fail(BICOS_B200_ERR_INVALID, "pitch smaller than a row");
+
+    const int nrows = row_end - row_begin;
+    PlaneTable t0, t1;
+    if (int rc = fill_table(t0, planes0, n, (size_t)row_begin * pitch_bytes))
+        return rc;
+    if (int rc = fill_table(t1, planes1, n, (size_t)row_begin * pitch_bytes))
+        return rc;
+
+    const int flags = search_flags(cfg);
+    const size_t dpw = desc_pitch_for(cols, K);
+    const size_t px = (size_t)nrows * cols;
+    CU(h->desc0.reserve(dpw * nrows * sizeof(uint32_t)));
+    CU(h->desc1.reserve(dpw * nrows * sizeof(uint32_t)));
+    CU(h->fwd.reserve(px * sizeof(int32_t)));
+    if (flags & FLAG_CONSISTENCY) {
+        CU(h->rev_first.reserve(px * sizeof(uint32_t)));
+        if (flags & FLAG_NODUPES)
+            CU(h->rev_last.reserve(px * sizeof(uint32_t)));
+    }
+
+    uint32_t* d0 = static_cast<uint32_t*>(h->desc0.ptr);
+    uint32_t* d1 = static_cast<uint32_t*>(h->desc1.ptr);
+    const int is_u16 = depth == BICOS_B200_16U;
+    CU(launch_transform(t0, n, nrows, cols, pitch_bytes, is_u16, cfg->mode != 0, K, d0, dpw, stream));
+    CU(launch_transform(t1, n, nrows, cols, pitch_bytes, is_u16, cfg->mode != 0, K, d1, dpw, stream));
+    h->launches += 2;
+
+    uint32_t* rf = static_cast<uint32_t*>(h->rev_first.ptr);
+    uint32_t* rl = static_cast<uint32_t*>(h->rev_last.ptr);
+    if (flags & FLAG_CONSISTENCY) {
+        CU(cudaMemsetAsync(rf, 0xFF, px * sizeof(uint32_t), stream));
+        if (flags & FLAG_NODUPES)
+            CU(cudaMemsetAsync(rl, 0xFF, px * sizeof(uint32_t), stream));
+    }
+    CU(launch_search(d0, d1, K, nrows, cols, dpw, flags, static_cast<int32_t*>(h->fwd.ptr), rf, rl, stream));
+    h->launches += 1;
+
+    char* disp_rows = static_cast<char*>(disparity) + (size_t)row_begin * disparity_pitch;
+    char* corr_rows = corrmap ? static_cast<char*>(corrmap) + (size_t)row_begin * corrmap_pitch : nullptr;
+    return do_refine(h, t0, t1, n, nrows, cols, pitch_bytes, depth, cfg, static_cast<int32_t*>(h->fwd.ptr), rf, rl,
+                     nullptr, disp_rows, disparity_pitch, corr_rows, corrmap_pitch, stream);
+}
+
+} // namespace
+
+extern "C" {
+
+const char* bicos_b200_last_error(void) {
+    return g_error.c_str();
+}
+
+int bicos_b200_device_count(void) {
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess)
+        return cuda_fail(err, "cudaGetDeviceCount");
+    return n;
+}
+
+int bicos_b200_create(bicos_b200_handle* out, int device) {
+    if (!out)
+        return fail(BICOS_B200_ERR_INVALID, "out is null");
+    *out = nullptr;
+    int count = 0;
+    CU(cudaGetDeviceCount(&count));
+    if (count <= 0)
+        return fail(BICOS_B200_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (device < 0)
+        CU(cudaGetDevice(&device));
+    if (device >= count)
+        return fail(BICOS_B200_ERR_INVALID, "device %d out of range (%d visible)", device, count);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(BICOS_B200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    bicos_b200_handle h = new (std::nothrow) bicos_b200_handle_s();
+    if (!h)
+        return fail(BICOS_B200_ERR_NOMEM, "out of host memory");
+    h->device = device;
+    *out = h;
+    return 0;
+}
+
+int bicos_b200_destroy(bicos_b200_handle h) {
+    if (!h)
+        return 0;
+    {
+        DeviceGuard g(h->device);
+        cudaDeviceSynchronize();
+        for (DeviceBuffer* b: { &h->desc0, &h->desc1, &h->fwd, &h->rev_first, &h->rev_last, &h->xs, &h->stage_in, &h->stage_disp, &h->stage_corr })
+            b->release();
+    }
+    delete h;
+    return 0;
+}
+
+int bicos_b200_descriptor_words(int n, int mode) {
+    if (n < 2)
+        return fail(BICOS_B200_ERR_INVALID, "need at least two images");
+    const int bits = descriptor_bits(n, mode != 0);
+    const int K = words_for_bits(bits);
+    if (K < 0 || n > MAX_IMAGES)
+        return fail(BICOS_B200_ERR_INVALID, "input stacks too large, would require %d bits", bits);
+    return K;
+}
+
+int bicos_b200_disparity_type(const bicos_b200_config* cfg) {
+    return cfg->nxcorr_threshold >= 0 ? BICOS_B200_32F : BICOS_B200_16S;
+}
+
+int bicos_b200_corrmap_type(const bicos_b200_config* cfg) {
+    if (cfg->nxcorr_threshold < 0)
+        return 0;
+    return cfg->precision != 0 ? BICOS_B200_64F : BICOS_B200_32F;
+}
+
+int bicos_b200_transform(bicos_b200_handle h, const void* const* planes, int n, int rows, int cols,
+                         size_t pitch_bytes, int depth, int mode, uint32_t* desc,
+                         size_t desc_pitch_words, void* stream) {
+    if (!h || !planes || !desc)
+        return fail(BICOS_B200_ERR_INVALID, "null argument");
+    bicos_b200_config cfg {};
+    cfg.nxcorr_threshold = -1.f;
+    cfg.mode = mode;
+    int K = 0;
+    if (int rc = validate_common(n, rows, cols, depth, &cfg, &K))
+        return rc;
+    if (desc_pitch_words < (size_t)cols * K || (desc_pitch_words % 4) != 0 || (reinterpret_cast<uintptr_t>(desc) % 16) != 0)
+        return fail(BICOS_B200_ERR_INVALID, "descriptor rows must be 16-byte aligned and hold cols*K words");
+    DeviceGuard g(h->device);
+    PlaneTable t;
+    if (int rc = fill_table(t, planes, n, 0))
+        return rc;
+    CU(launch_transform(t, n, rows, cols, pitch_bytes, depth == BICOS_B200_16U, mode != 0, K, desc, desc_pitch_words, static_cast<cudaStream_t>(stream)));
+    h->launches += 1;
+    return 0;
+}
+
+int bicos_b200_search(bicos_b200_handle h, const uint32_t* desc0, const uint32_t* desc1, int K,
+                      int rows, int cols, size_t desc_pitch_words, int flags, int32_t* fwd_best,
+                      uint32_t* rev_first, uint32_t* rev_last, void* stream) {
+    if (!h || !desc0 || !desc1 || !fwd_best)
+        return fail(BICOS_B200_ERR_INVALID, "null argument");
+    if (K != 1 && K != 2 && K != 4 && K != 8)
+        return fail(BICOS_B200_ERR_INVALID, "K must be 1, 2, 4 or 8");
+    if (flags < 0 || flags > 3)
+        return fail(BICOS_B200_ERR_INVALID, "bad flags");
+    if (rows <= 0 || cols <= 0 || cols > 32767)
+        return fail(BICOS_B200_ERR_INVALID, "bad image size");
+    if ((flags & FLAG_CONSISTENCY) && (!rev_first || ((flags & FLAG_NODUPES) && !rev_last)))
+        return fail(BICOS_B200_ERR_INVALID, "consistency search needs rev_first (and rev_last with no_dupes)");
+    if (desc_pitch_words < (size_t)cols * K || (desc_pitch_words % 4) != 0)
+        return fail(BICOS_B200_ERR_INVALID, "descriptor rows must be 16-byte aligned and hold cols*K words");
+    DeviceGuard g(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t px = (size_t)rows * cols;
+    if (flags & FLAG_CONSISTENCY) {
+        CU(cudaMemsetAsync(rev_first, 0xFF, px * sizeof(uint32_t), s));
+        if (flags & FLAG_NODUPES)
+            CU(cudaMemsetAsync(rev_last, 0xFF, px * sizeof(uint32_t), s));
+    }
+    CU(launch_search(desc0, desc1, K, rows, cols, desc_pitch_words, flags, fwd_best, rev_first, rev_last, s));
+    h->launches += 1;
+    return 0;
+}
+
+int bicos_b200_refine(bicos_b200_handle h, const void* const* planes0, const void* const* planes1,
+                      int n, int rows, int cols, size_t pitch_bytes, int depth,
+                      const bicos_b200_config* cfg, const int32_t* fwd_best,
+                      const uint32_t* rev_first, const uint32_t* rev_last, int16_t* raw_disp_out,
+                      void* disparity, size_t disparity_pitch_bytes, void* corrmap,
+                      size_t corrmap_pitch_bytes, void* stream) {
+    if (!h || !planes0 || !planes1 || !fwd_best || !disparity)
+        return fail(BICOS_B200_ERR_INVALID, "null argument");
+    if (int rc = validate_common(n, rows, cols, depth, cfg, nullptr))
+        return rc;
+    if (cfg->variant_type != 0 && (!rev_first || (cfg->no_dupes && !rev_last)))
+        return fail(BICOS_B200_ERR_INVALID, "consistency postfilter needs rev_first (and rev_last with no_dupes)");
+    DeviceGuard g(h->device);
+    PlaneTable t0, t1;
+    if (int rc = fill_table(t0, planes0, n, 0))
+        return rc;
+    if (int rc = fill_table(t1, planes1, n, 0))
+        return rc;
+    return do_refine(h, t0, t1, n, rows, cols, pitch_bytes, depth, cfg, fwd_best, rev_first, rev_last, raw_disp_out,
+                     disparity, disparity_pitch_bytes, corrmap, corrmap_pitch_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int bicos_b200_match(bicos_b200_handle h, const void* const* planes0, const void* const* planes1,
+                     int n, int rows, int cols, size_t pitch_bytes, int depth,
+                     const bicos_b200_config* cfg, void* disparity, size_t disparity_pitch_bytes,
+                     void* corrmap, size_t corrmap_pitch_bytes, void* stream) {
+    if (!h)
+        return fail(BICOS_B200_ERR_INVALID, "null handle");
+    DeviceGuard g(h->device);
+    return do_match(h, planes0, planes1, n, rows, cols, pitch_bytes, depth, cfg, 0, rows, disparity,
+                    disparity_pitch_bytes, corrmap, corrmap_pitch_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int bicos_b200_match_rows(bicos_b200_handle h, const void* const* planes0,
+                          const void* const* planes1, int n, int rows, int cols, size_t pitch_bytes,
+                          int depth, const bicos_b200_config* cfg, int row_begin, int row_end,
+                          void* disparity, size_t disparity_pitch_bytes, void* corrmap,
+                          size_t corrmap_pitch_bytes, void* stream) {
+    if (!h)
+        return fail(BICOS_B200_ERR_INVALID, "null handle");
+    DeviceGuard g(h->device);
+    return do_match(h, planes0, planes1, n, rows, cols, pitch_bytes, depth, cfg, row_begin, row_end, disparity,
+                    disparity_pitch_bytes, corrmap, corrmap_pitch_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int bicos_b200_match_host(bicos_b200_handle h, const void* const* host_planes0,
+                          const void* const* host_planes1, int n, int rows, int cols, int depth,
+                          const bicos_b200_config* cfg, void* host_disparity, void* host_corrmap) {
+    if (!h || !host_planes0 || !host_planes1 || !host_disparity)
+        return fail(BICOS_B200_ERR_INVALID, "null argument");
+    if (int rc = validate_common(n, rows, cols, depth, cfg, nullptr))
+        return rc;
+    DeviceGuard g(h->device);
+    cudaStream_t stream = nullptr;
+
+    const size_t eb = depth_bytes(depth);
+    const size_t row_bytes = (size_t)cols * eb;
+    const size_t pitch = (row_bytes + 15) & ~(size_t)15;
+    const size_t plane_bytes = pitch * rows;
+    CU(h->stage_in.reserve(plane_bytes * 2 * n));
+    std::vector<const void*> dev0(n), dev1(n);
+    char* base = static_cast<char*>(h->stage_in.ptr);
+    for (int i = 0; i < n; ++i) {
+        if (!host_planes0[i] || !host_planes1[i])
+            return fail(BICOS_B200_ERR_INVALID, "image %d is null", i);
+        dev0[i] = base + plane_bytes * i;
+        dev1[i] = base + plane_bytes * (n + i);
+        CU(cudaMemcpy2DAsync(const_cast<void*>(dev0[i]), pitch, host_planes0[i], row_bytes, row_bytes, rows, cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpy2DAsync(const_cast<void*>(dev1[i]), pitch, host_planes1[i], row_bytes, row_bytes, rows, cudaMemcpyHostToDevice, stream));
+    }
+
+    const size_t disp_eb = cfg->nxcorr_threshold >= 0 ? 4 : 2;
+    const size_t corr_eb = cfg->precision != 0 ? 8 : 4;
+    const bool want_corr = host_corrmap && cfg->nxcorr_threshold >= 0;
+    CU(h->stage_disp.reserve((size_t)rows * cols * disp_eb));
+    if (want_corr)
+        CU(h->stage_corr.reserve((size_t)rows * cols * corr_eb));
+
+    if (int rc = do_match(h, dev0.data(), dev1.data(), n, rows, cols, pitch, depth, cfg, 0, rows, h->stage_disp.ptr,
+                          (size_t)cols * disp_eb, want_corr ? h->stage_corr.ptr : nullptr, (size_t)cols * corr_eb, stream))
+        return rc;
+
+    CU(cudaMemcpyAsync(host_disparity, h->stage_disp.ptr, (size_t)rows * cols * disp_eb, cudaMemcpyDeviceToHost, stream));
+    if (want_corr)
+        CU(cudaMemcpyAsync(host_corrmap, h->stage_corr.ptr, (size_t)rows * cols * corr_eb, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+int bicos_b200_synchronize(bicos_b200_handle h, void* stream) {
+    if (!h)
+        return fail(BICOS_B200_ERR_INVALID, "null handle");
+    DeviceGuard g(h->device);
+    CU(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+long long bicos_b200_kernel_launches(bicos_b200_handle h) {
+    return h ? h->launches : 0;
+}
+
+} // extern "C"

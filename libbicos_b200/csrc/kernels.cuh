@@ -1,0 +1,98 @@
+// Internal launch interface between the C-ABI layer (cabi.cu) and the three sm_100a
+// kernels of the BICOS::match hot path. Device pointers only; every function enqueues
+// on `stream` and returns the CUDA status of the launch.
+//
+// Data layout in HBM:
+//   input stacks   n planar single-channel images per side, each [rows][pitch] bytes,
+//                  passed as a by-value table of plane pointers (no host-mapped tables)
+//   descriptors    [rows][desc_pitch_words] uint32, K = 1/2/4/8 words per pixel,
+//                  bit i of a descriptor = bit i%32 of word i/32; rows start 16 B aligned
+//   search result  fwd_best [rows][cols] int32: best right column or -1 (no unique match)
+//                  rev_first/rev_last [rows][cols] uint32 keys (cost<<16 | col0) resp.
+//                  (cost<<16 | 65535-col0): column-wise minima for the consistency check
+//   outputs        disparity int16 or float32, corrmap float32 or float64, both pitched
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bicos_b200 {
+
+constexpr int MAX_IMAGES = 65; // 4n-6 <= 256 bits (reference src/impl/cuda.cu:107 "Bad number of images")
+constexpr int FLAG_NODUPES = 1; // reference include/impl/common.hpp:46
+constexpr int FLAG_CONSISTENCY = 2; // reference include/impl/common.hpp:47
+constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
+
+struct PlaneTable {
+    const void* p[MAX_IMAGES];
+};
+
+struct RefineParams {
+    int n, rows, cols;
+    size_t in_pitch; // bytes, same for every plane of both stacks
+    int is_u16;
+    int is_double;
+    int consistency; // postfilter: left-right check against rev_first / rev_last
+    int nodupes_reverse; // consistency with no_dupes: reverse search must be unique too
+    int max_lr_diff;
+    int has_threshold;
+    float threshold;
+    int has_minvar;
+    float minvar_times_n; // min_variance * n, in float (reference src/impl/cpu.cpp:127)
+    int subpixel;
+    int nsteps; // number of x values of the float loop x=-1; x<=1; x+=step
+    const float* xs; // device array [nsteps] with exactly those float values
+    const int32_t* fwd_best;
+    const uint32_t* rev_first;
+    const uint32_t* rev_last;
+    int16_t* raw_out; // optional [rows][cols] dense: postfilter result before the NXC test
+    void* disp_out; // int16 if !has_threshold else float32
+    size_t disp_pitch; // bytes
+    void* corr_out; // float32 or float64, may be null
+    size_t corr_pitch; // bytes
+};
+
+// kernel 1: temporal descriptor transform (reference a2/a3/a4)
+cudaError_t launch_transform(
+    const PlaneTable& planes,
+    int n,
+    int rows,
+    int cols,
+    size_t in_pitch,
+    int is_u16,
+    int mode_full,
+    int K,
+    uint32_t* desc,
+    size_t desc_pitch_words,
+    cudaStream_t stream
+);
+
+// kernel 2: row-wise Hamming argmin, forward (per left pixel) and, with
+// FLAG_CONSISTENCY, the column-wise minima of the same W x W cost tile (reference a5/a6/a7).
+// rev_first / rev_last must be pre-filled with KEY_NONE by the caller.
+cudaError_t launch_search(
+    const uint32_t* desc0,
+    const uint32_t* desc1,
+    int K,
+    int rows,
+    int cols,
+    size_t desc_pitch_words,
+    int flags,
+    int32_t* fwd_best,
+    uint32_t* rev_first,
+    uint32_t* rev_last,
+    cudaStream_t stream
+);
+
+// kernel 3: postfilter (no-duplicates / left-right consistency) fused with the NXC
+// agree / agree_subpixel refinement (reference a7 tail, a8, a9, a10, a11)
+cudaError_t launch_refine(
+    const PlaneTable& stack0,
+    const PlaneTable& stack1,
+    const RefineParams& prm,
+    cudaStream_t stream
+);
+
+int search_smem_bytes(int K, int cols, int flags);
+
+} // namespace bicos_b200

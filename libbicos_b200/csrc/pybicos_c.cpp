@@ -1,0 +1,144 @@
+// The Python-facing C ABI (include/pybicos_c.h): host images in, malloc'ed host results out.
+// Behavioural twin of the reference's src/pybicos_c.cpp:92-209, on bicos_b200_match_host().
+
+#include "../../include/pybicos_c.h"
+#include "../../include/bicos_b200.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <limits>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string t_error;
+std::mutex g_mutex; // one shared workspace per process; matches are serialised through it
+bicos_b200_handle g_handle = nullptr;
+
+BicosResult* fail(const std::string& msg) {
+    t_error = msg;
+    return nullptr;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* BICOS_LastError(void) {
+    return t_error.c_str();
+}
+
+BicosConfig* BICOS_CreateDefaultConfig(void) {
+    BicosConfig* c = new (std::nothrow) BicosConfig();
+    if (!c)
+        return nullptr;
+    c->nxcorr_threshold = 0.5f;
+    c->subpixel_step = -1.0f;
+    c->min_variance = -1.0f;
+    c->mode = 0;
+    c->precision = 0;
+    c->variant_type = 0;
+    c->max_lr_diff = 1;
+    c->no_dupes = 0;
+    return c;
+}
+
+void BICOS_FreeConfig(BicosConfig* config) {
+    delete config;
+}
+
+void BICOS_FreeResult(BicosResult* result) {
+    if (!result)
+        return;
+    std::free(result->disparity_data);
+    std::free(result->corrmap_data);
+    delete result;
+}
+
+BicosResult* BICOS_Match(void** stack0_data, int* stack0_rows, int* stack0_cols, int* stack0_types,
+                         int stack0_size, void** stack1_data, int* stack1_rows, int* stack1_cols,
+                         int* stack1_types, int stack1_size, BicosConfig* config) {
+    try {
+        if (!config || !stack0_data || !stack1_data || !stack0_rows || !stack0_cols || !stack0_types
+            || !stack1_rows || !stack1_cols || !stack1_types)
+            return fail("null argument");
+        if (stack0_size < 2 || stack1_size < 2)
+            return fail("need at least two images");
+        if (stack0_size != stack1_size)
+            return fail("stacks differ in length");
+        const int rows = stack0_rows[0], cols = stack0_cols[0], depth = stack0_types[0] & 7;
+        for (int i = 0; i < stack0_size; ++i)
+            if (stack0_rows[i] != rows || stack0_cols[i] != cols || (stack0_types[i] & 7) != depth
+                || stack1_rows[i] != rows || stack1_cols[i] != cols || (stack1_types[i] & 7) != depth)
+                return fail("images differ in size or type");
+
+        bicos_b200_config cfg;
+        cfg.nxcorr_threshold = config->nxcorr_threshold;
+        cfg.subpixel_step = config->subpixel_step;
+        cfg.min_variance = config->min_variance;
+        cfg.mode = config->mode;
+        cfg.precision = config->precision;
+        cfg.variant_type = config->variant_type;
+        cfg.max_lr_diff = config->max_lr_diff;
+        cfg.no_dupes = config->no_dupes;
+
+        const int disp_type = bicos_b200_disparity_type(&cfg);
+        const int corr_type = bicos_b200_corrmap_type(&cfg);
+        const size_t px = (size_t)rows * cols;
+        const size_t disp_bytes = px * (disp_type == BICOS_B200_16S ? 2 : 4);
+        const size_t corr_bytes = corr_type == 0 ? 0 : px * (corr_type == BICOS_B200_64F ? 8 : 4);
+
+        BicosResult* res = new (std::nothrow) BicosResult();
+        if (!res)
+            return fail("out of memory");
+        res->disparity_data = std::malloc(disp_bytes ? disp_bytes : 1);
+        res->corrmap_data = corr_bytes ? std::malloc(corr_bytes) : nullptr;
+        if (!res->disparity_data || (corr_bytes && !res->corrmap_data)) {
+            BICOS_FreeResult(res);
+            return fail("out of memory");
+        }
+
+        int rc;
+        {
+            std::lock_guard<std::mutex> lock(g_mutex);
+            if (!g_handle) {
+                rc = bicos_b200_create(&g_handle, -1);
+                if (rc != 0) {
+                    BICOS_FreeResult(res);
+                    return fail(bicos_b200_last_error());
+                }
+            }
+            rc = bicos_b200_match_host(g_handle, stack0_data, stack1_data, stack0_size, rows, cols, depth, &cfg,
+                                       res->disparity_data, res->corrmap_data);
+        }
+        if (rc != 0) {
+            BICOS_FreeResult(res);
+            return fail(bicos_b200_last_error());
+        }
+        res->disparity_rows = rows;
+        res->disparity_cols = cols;
+        res->disparity_type = disp_type;
+        // like the reference, an unset threshold yields an empty corrmap (type 0, no data)
+        res->corrmap_rows = corr_type ? rows : 0;
+        res->corrmap_cols = corr_type ? cols : 0;
+        res->corrmap_type = corr_type;
+        return res;
+    } catch (const std::exception& e) {
+        return fail(e.what());
+    } catch (...) {
+        return fail("unknown error");
+    }
+}
+
+float BICOS_InvalidDisparityFloat(void) {
+    return std::numeric_limits<float>::quiet_NaN();
+}
+
+int16_t BICOS_InvalidDisparityInt16(void) {
+    return std::numeric_limits<int16_t>::lowest();
+}
+
+} // extern "C"

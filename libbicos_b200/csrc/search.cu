@@ -1,0 +1,331 @@
+// Kernel 2 of the BICOS::match hot path: row-wise brute-force Hamming argmin.
+//
+// Replaces (behaviour, not structure):
+//   reference include/impl/cpu/bicos.hpp:29-76   ham / bicos_search
+//   reference include/impl/cuda/bicos.cuh:50-176 bicos_search / bicos_kernel[_smem]
+//
+// One CTA = one work unit = (image row, block of UNIT left pixels). Each thread keeps A
+// left descriptors in registers and scans the whole right row, which is staged through
+// shared memory in chunks and read with warp-uniform (broadcast) vector loads.
+//
+// Exactness without the reference's serial scan:
+//  * key = cost << 16 | column. min(key) over any partition of the row is the lowest cost
+//    and, among equal costs, the lowest column: the reference's "first strict minimum"
+//    (bicos.hpp:57-60).
+//  * NODUPES (bicos.hpp:62-71: any later tie with the final minimum invalidates): a second
+//    key cost << 16 | (65535 - column) finds the LAST column with the minimal cost; a
+//    duplicate exists iff first != last. Both are plain min-reductions, so they merge
+//    associatively across lanes, chunks and CTAs.
+//  * CONSISTENCY (bicos.hpp:99-106 runs a second full search from the matched right pixel
+//    over the left row): Hamming distance is symmetric, so the same W x W cost tile feeds the
+//    column-wise minima. Each warp min-reduces its 32*A costs for the current right column
+//    with REDUX and merges into a per-CTA shared array, which is flushed to global memory
+//    with atomicMin. The postfilter (refine.cu) then only looks up rev[best_col1].
+//
+// Popcount pipe is the bound (16 POPC/clk/SM): carry-save compression brings a 128-bit
+// distance from 4 to 3 POPC and a 256-bit distance from 8 to 4 POPC.
+
+#include "kernels.cuh"
+
+namespace bicos_b200 {
+namespace {
+
+constexpr int THREADS = 128;
+constexpr int A = 4; // left descriptors per thread
+constexpr int UNIT = THREADS * A; // left pixels per CTA
+constexpr int CHUNK_BYTES = 16 * 1024; // right-row descriptor bytes staged per pass
+
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+template<int K>
+struct Desc {
+    uint32_t w[K];
+};
+
+template<int K>
+__device__ __forceinline__ Desc<K> load_desc(const uint32_t* p) {
+    Desc<K> d;
+    if constexpr (K == 1) {
+        d.w[0] = *p;
+    } else if constexpr (K == 2) {
+        const uint2 v = *reinterpret_cast<const uint2*>(p);
+        d.w[0] = v.x;
+        d.w[1] = v.y;
+    } else {
+#pragma unroll
+        for (int q = 0; q < K / 4; ++q) {
+            const uint4 v = reinterpret_cast<const uint4*>(p)[q];
+            d.w[4 * q + 0] = v.x;
+            d.w[4 * q + 1] = v.y;
+            d.w[4 * q + 2] = v.z;
+            d.w[4 * q + 3] = v.w;
+        }
+    }
+    return d;
+}
+
+// popcount(l ^ r) over K words (reference ham(), bicos.hpp:29-48)
+template<int K>
+__device__ __forceinline__ uint32_t hamming(const Desc<K>& l, const Desc<K>& r) {
+    uint32_t x[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+        x[k] = l.w[k] ^ r.w[k];
+    if constexpr (K == 1) {
+        return __popc(x[0]);
+    } else if constexpr (K == 2) {
+        return __popc(x[0]) + __popc(x[1]);
+    } else if constexpr (K == 4) {
+        // full adder over three words: ones in s, twos in c -> 3 POPC instead of 4
+        const uint32_t s = xor3(x[0], x[1], x[2]);
+        const uint32_t c = maj3(x[0], x[1], x[2]);
+        return __popc(s) + __popc(x[3]) + 2 * __popc(c);
+    } else {
+        // carry-save tree over eight words -> 4 POPC instead of 8
+        const uint32_t s1 = xor3(x[0], x[1], x[2]), c1 = maj3(x[0], x[1], x[2]);
+        const uint32_t s2 = xor3(x[3], x[4], x[5]), c2 = maj3(x[3], x[4], x[5]);
+        const uint32_t s3 = xor3(s1, s2, x[6]), c3 = maj3(s1, s2, x[6]);
+        // ones: s3, x7; twos: c1 c2 c3 -> one more full adder gives twos t and fours f
+        const uint32_t t = xor3(c1, c2, c3), f = maj3(c1, c2, c3);
+        return __popc(s3) + __popc(x[7]) + 2 * __popc(t) + 4 * __popc(f);
+    }
+}
+
+template<int K, int FLAGS>
+__global__ void __launch_bounds__(THREADS) search_kernel(
+    const uint32_t* __restrict__ desc0,
+    const uint32_t* __restrict__ desc1,
+    int cols,
+    size_t pitch_words,
+    int chunk, // right descriptors staged per pass
+    int units_per_row,
+    int32_t* __restrict__ fwd_best,
+    uint32_t* __restrict__ rev_first,
+    uint32_t* __restrict__ rev_last
+) {
+    constexpr bool NODUPES = (FLAGS & FLAG_NODUPES) != 0;
+    constexpr bool REVERSE = (FLAGS & FLAG_CONSISTENCY) != 0;
+
+    extern __shared__ uint4 smem_raw[];
+    uint32_t* const s_right = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* const s_colf = s_right + (size_t)chunk * K;
+    uint32_t* const s_coll = s_colf + chunk;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int row = blockIdx.x / units_per_row;
+    const int unit = blockIdx.x - row * units_per_row;
+
+    const uint32_t* const row0 = desc0 + (size_t)row * pitch_words;
+    const uint32_t* const row1 = desc1 + (size_t)row * pitch_words;
+
+    Desc<K> l[A];
+    uint32_t icol[A], icol_rev[A];
+    uint32_t mf[A], ml[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        const int i = unit * UNIT + a * THREADS + tid;
+        const bool valid = i < cols;
+        l[a] = load_desc<K>(row0 + (size_t)(valid ? i : cols - 1) * K);
+        // lanes past the end of the row carry bit 31 so that they never win a column minimum
+        icol[a] = valid ? (uint32_t)i : (0x80000000u | (uint32_t)i);
+        icol_rev[a] = valid ? (uint32_t)(65535 - i) : (0x80000000u | (uint32_t)i);
+        mf[a] = KEY_NONE;
+        ml[a] = KEY_NONE;
+    }
+
+    for (int j0 = 0; j0 < cols; j0 += chunk) {
+        const int cnt = min(chunk, cols - j0);
+        __syncthreads(); // previous chunk fully consumed and flushed
+
+        // stage the right descriptors [j0, j0+cnt) (rows are 16 B aligned and padded)
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(row1 + (size_t)j0 * K);
+            const int nvec = (cnt * K + 3) / 4;
+            for (int v = tid; v < nvec; v += THREADS)
+                smem_raw[v] = src[v];
+            if constexpr (REVERSE) {
+                for (int v = tid; v < cnt; v += THREADS) {
+                    s_colf[v] = KEY_NONE;
+                    if constexpr (NODUPES)
+                        s_coll[v] = KEY_NONE;
+                }
+            }
+        }
+        __syncthreads();
+
+#pragma unroll 2
+        for (int jj = 0; jj < cnt; ++jj) {
+            const Desc<K> r = load_desc<K>(s_right + (size_t)jj * K); // warp-uniform: broadcast
+            const uint32_t j = (uint32_t)(j0 + jj);
+            const uint32_t jrev = 65535u - j;
+            uint32_t ck = KEY_NONE, ckl = KEY_NONE;
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                const uint32_t cost16 = hamming<K>(l[a], r) << 16;
+                mf[a] = min(mf[a], cost16 + j);
+                if constexpr (NODUPES)
+                    ml[a] = min(ml[a], cost16 + jrev);
+                if constexpr (REVERSE) {
+                    ck = min(ck, cost16 + icol[a]);
+                    if constexpr (NODUPES)
+                        ckl = min(ckl, cost16 + icol_rev[a]);
+                }
+            }
+            if constexpr (REVERSE) {
+                ck = __reduce_min_sync(0xFFFFFFFFu, ck);
+                if constexpr (NODUPES)
+                    ckl = __reduce_min_sync(0xFFFFFFFFu, ckl);
+                if (lane == 0) {
+                    atomicMin(&s_colf[jj], ck);
+                    if constexpr (NODUPES)
+                        atomicMin(&s_coll[jj], ckl);
+                }
+            }
+        }
+
+        if constexpr (REVERSE) {
+            __syncthreads();
+            uint32_t* const gf = rev_first + (size_t)row * cols + j0;
+            uint32_t* const gl = rev_last + (size_t)row * cols + j0;
+            for (int v = tid; v < cnt; v += THREADS) {
+                atomicMin(gf + v, s_colf[v]);
+                if constexpr (NODUPES)
+                    atomicMin(gl + v, s_coll[v]);
+            }
+        }
+    }
+
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        const int i = unit * UNIT + a * THREADS + tid;
+        if (i < cols) {
+            int best = (int)(mf[a] & 0xFFFFu);
+            if constexpr (NODUPES)
+                if ((ml[a] & 0xFFFFu) != 65535u - (uint32_t)best)
+                    best = -1; // at least two columns attain the minimum
+            fwd_best[(size_t)row * cols + i] = best;
+        }
+    }
+}
+
+int chunk_for(int K, int cols) {
+    const int cap = CHUNK_BYTES / (4 * K);
+    const int padded = (cols + 3) & ~3;
+    return padded < cap ? padded : cap;
+}
+
+template<int K, int FLAGS>
+cudaError_t launch_one(
+    const uint32_t* desc0,
+    const uint32_t* desc1,
+    int rows,
+    int cols,
+    size_t pitch_words,
+    int32_t* fwd_best,
+    uint32_t* rev_first,
+    uint32_t* rev_last,
+    cudaStream_t stream
+) {
+    const int chunk = chunk_for(K, cols);
+    const int smem = search_smem_bytes(K, cols, FLAGS);
+    cudaError_t err = cudaFuncSetAttribute(
+        search_kernel<K, FLAGS>,
+        cudaFuncAttributeMaxDynamicSharedMemorySize,
+        smem
+    );
+    if (err != cudaSuccess)
+        return err;
+    const int units_per_row = (cols + UNIT - 1) / UNIT;
+    const long long grid = (long long)rows * units_per_row;
+    if (grid <= 0 || grid > 0x7FFFFFFFLL)
+        return cudaErrorInvalidConfiguration;
+    search_kernel<K, FLAGS><<<(unsigned)grid, THREADS, smem, stream>>>(
+        desc0,
+        desc1,
+        cols,
+        pitch_words,
+        chunk,
+        units_per_row,
+        fwd_best,
+        rev_first,
+        rev_last
+    );
+    return cudaGetLastError();
+}
+
+template<int K>
+cudaError_t launch_k(
+    const uint32_t* desc0,
+    const uint32_t* desc1,
+    int rows,
+    int cols,
+    size_t pitch_words,
+    int flags,
+    int32_t* fwd_best,
+    uint32_t* rev_first,
+    uint32_t* rev_last,
+    cudaStream_t stream
+) {
+    switch (flags) {
+        case FLAG_NODUPES:
+            return launch_one<K, FLAG_NODUPES>(desc0, desc1, rows, cols, pitch_words, fwd_best, rev_first, rev_last, stream);
+        case FLAG_CONSISTENCY:
+            return launch_one<K, FLAG_CONSISTENCY>(desc0, desc1, rows, cols, pitch_words, fwd_best, rev_first, rev_last, stream);
+        case FLAG_NODUPES | FLAG_CONSISTENCY:
+            return launch_one<K, FLAG_NODUPES | FLAG_CONSISTENCY>(desc0, desc1, rows, cols, pitch_words, fwd_best, rev_first, rev_last, stream);
+        case 0: // plain first-minimum search (building block, not reachable from Config)
+            return launch_one<K, 0>(desc0, desc1, rows, cols, pitch_words, fwd_best, rev_first, rev_last, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+} // namespace
+
+int search_smem_bytes(int K, int cols, int flags) {
+    const int chunk = chunk_for(K, cols);
+    int bytes = chunk * K * 4;
+    if (flags & FLAG_CONSISTENCY)
+        bytes += chunk * 4 * ((flags & FLAG_NODUPES) ? 2 : 1);
+    return bytes;
+}
+
+cudaError_t launch_search(
+    const uint32_t* desc0,
+    const uint32_t* desc1,
+    int K,
+    int rows,
+    int cols,
+    size_t desc_pitch_words,
+    int flags,
+    int32_t* fwd_best,
+    uint32_t* rev_first,
+    uint32_t* rev_last,
+    cudaStream_t stream
+) {
+    if (rows <= 0 || cols <= 0 || cols > 32767)
+        return cudaErrorInvalidValue;
+    switch (K) {
+        case 1:
+            return launch_k<1>(desc0, desc1, rows, cols, desc_pitch_words, flags, fwd_best, rev_first, rev_last, stream);
+        case 2:
+            return launch_k<2>(desc0, desc1, rows, cols, desc_pitch_words, flags, fwd_best, rev_first, rev_last, stream);
+        case 4:
+            return launch_k<4>(desc0, desc1, rows, cols, desc_pitch_words, flags, fwd_best, rev_first, rev_last, stream);
+        case 8:
+            return launch_k<8>(desc0, desc1, rows, cols, desc_pitch_words, flags, fwd_best, rev_first, rev_last, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+} // namespace bicos_b200

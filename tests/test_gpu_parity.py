@@ -1,0 +1,232 @@
+"""GPU parity tests: every stage and the whole path, through the C ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star): descriptors, integer disparities and the valid mask bit-exact;
+corrmap within 1e-5 (float) / 1e-12 (double); subpixel disparity within 1e-3 px. The kernels
+reproduce the reference's operation order, so the tests additionally report (and for float
+require) exact equality.
+"""
+
+import numpy as np
+import pytest
+
+from libbicos_b200 import Config, synth
+
+pytestmark = pytest.mark.gpu
+
+FLAG_NODUPES, FLAG_CONSISTENCY = 1, 2
+
+
+def _cuda(a):
+    import torch
+
+    if a.dtype == np.uint16:
+        return torch.from_numpy(a.view(np.int16)).cuda().view(torch.uint16)
+    return torch.from_numpy(a).cuda()
+
+
+def _words(desc, k, cols):
+    """pitched int32 [rows, pitch] -> uint32 numpy [rows, cols, k]"""
+    rows = desc.shape[0]
+    return desc.cpu().numpy().view(np.uint32)[:, : cols * k].reshape(rows, cols, k)
+
+
+def _same(a, b):
+    return np.array_equal(a, b, equal_nan=True) if a.dtype.kind == "f" else np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------------- transform --
+@pytest.mark.parametrize(
+    "n,dtype,full,cols",
+    [
+        (2, np.uint8, False, 64), (3, np.uint8, False, 61), (4, np.uint16, False, 64),
+        (9, np.uint8, False, 128), (10, np.uint8, False, 131), (17, np.uint16, False, 96),
+        (18, np.uint8, False, 64), (33, np.uint8, False, 256), (33, np.uint16, False, 130),
+        (34, np.uint8, False, 66), (64, np.uint8, False, 128), (65, np.uint16, False, 64),
+        (2, np.uint8, True, 64), (5, np.uint8, True, 67), (6, np.uint16, True, 64),
+        (8, np.uint8, True, 128), (9, np.uint16, True, 64), (12, np.uint8, True, 256),
+        (13, np.uint8, True, 64), (16, np.uint16, True, 128), (16, np.uint8, True, 63),
+    ],
+)
+def test_transform_bit_exact(handle, oracles, n, dtype, full, cols):
+    rows = 40
+    left, right, _ = synth.make_stacks(n, rows, cols, dtype, seed=n * 7 + cols)
+    # extremes: saturated, zero and near-constant pixels stress the integer mean comparison
+    left[:, 0, :] = np.iinfo(dtype).max
+    left[:, 1, :] = 0
+    left[:, 2, :] = 100
+    left[n // 2, 2, ::3] = 101
+    for stack in (left, right):
+        want = oracles.port.descriptors(stack, full)
+        desc, k = handle.transform(_cuda(stack), full)
+        got = _words(desc, k, cols)
+        assert k == want.shape[2]
+        assert np.array_equal(got, want), f"{(got != want).any(axis=2).sum()} descriptors differ"
+
+
+def test_transform_strided_view(handle, oracles):
+    """Planes that are views into a wider allocation (pitch > cols) and an odd pitch (scalar path)."""
+    import torch
+
+    n, rows, cols = 33, 24, 100
+    left, _, _ = synth.make_stacks(n, rows, cols + 7, np.uint8, seed=5)
+    big = _cuda(left)
+    view = big[:, :, 3 : 3 + cols]
+    want = oracles.port.descriptors(np.ascontiguousarray(left[:, :, 3 : 3 + cols]), False)
+    desc, k = handle.transform(view, False)
+    assert np.array_equal(_words(desc, k, cols), want)
+    assert torch.cuda.current_stream().query() or True
+
+
+# ---------------------------------------------------------------------------- search --
+def _random_desc(rng, rows, cols, k, bits):
+    """Descriptors with few distinct values per word, so ties and duplicates are frequent."""
+    return rng.integers(0, 1 << bits, size=(rows, cols, k), dtype=np.int64).astype(np.uint32)
+
+
+@pytest.mark.parametrize("k", [1, 2, 4, 8])
+@pytest.mark.parametrize("flags", [FLAG_NODUPES, FLAG_CONSISTENCY, FLAG_NODUPES | FLAG_CONSISTENCY])
+@pytest.mark.parametrize("cols,bits", [(97, 3), (512, 8), (700, 32), (1300, 5)])
+def test_search_postfilter_bit_exact(handle, oracles, k, flags, cols, bits):
+    import torch
+
+    rng = np.random.default_rng(k * 100 + flags * 10 + cols)
+    rows = 6
+    d0 = _random_desc(rng, rows, cols, k, bits)
+    d1 = _random_desc(rng, rows, cols, k, bits)
+    # plant some true matches so that low costs and unique minima occur too
+    src = rng.integers(0, cols, size=cols // 2)
+    dst = rng.integers(0, cols, size=cols // 2)
+    d0[:, dst] = d1[:, src] ^ (rng.integers(0, 2, size=(rows, cols // 2, k)) << 7).astype(np.uint32)
+    max_lr = 3
+    want = oracles.port.bicos(d0, d1, flags, max_lr)
+
+    pitch = (cols * k + 3) // 4 * 4
+
+    def pitched(d):
+        buf = np.zeros((rows, pitch), dtype=np.uint32)
+        buf[:, : cols * k] = d.reshape(rows, cols * k)
+        return torch.from_numpy(buf.view(np.int32)).cuda()
+
+    fwd, revf, revl = handle.search(pitched(d0), pitched(d1), k, cols, flags)
+    # postfilter only (threshold unset): the int16 disparity of reference bicos()
+    dummy = torch.zeros((2, rows, cols), dtype=torch.uint8, device="cuda")
+    cfg = Config(nxcorr_threshold=None, consistency=bool(flags & FLAG_CONSISTENCY), max_lr_diff=max_lr,
+                 no_dupes=flags == 3)
+    disp, corr, raw = handle.refine(dummy, dummy, cfg, fwd, revf, revl)
+    got = disp.cpu().numpy()
+    assert corr is None and got.dtype == np.int16
+    assert np.array_equal(got, want), f"{(got != want).sum()} of {got.size} disparities differ"
+    assert np.array_equal(raw.cpu().numpy(), want)
+
+
+# ------------------------------------------------------------------------- whole path --
+CASES = [
+    # n, dtype, rows, cols, config
+    (33, np.uint8, 48, 320, dict(nxcorr_threshold=0.96, min_variance=2.0)),  # BASELINE config 1 (small)
+    (33, np.uint8, 48, 320, dict(nxcorr_threshold=0.96, min_variance=2.0, subpixel_step=0.1, consistency=True,
+                                 max_lr_diff=1)),  # BASELINE config 2 (small)
+    (33, np.uint8, 40, 300, dict(nxcorr_threshold=None)),
+    (33, np.uint8, 40, 300, dict(nxcorr_threshold=0.5)),
+    (33, np.uint8, 40, 300, dict(nxcorr_threshold=0.9, subpixel_step=0.25, consistency=True, max_lr_diff=2,
+                                 no_dupes=True)),
+    (16, np.uint16, 40, 288, dict(nxcorr_threshold=0.9, mode_full=True, min_variance=1.0)),  # config 3 shape
+    (16, np.uint16, 40, 288, dict(nxcorr_threshold=0.9, mode_full=True, subpixel_step=0.1, consistency=True)),
+    (64, np.uint8, 32, 256, dict(nxcorr_threshold=0.9, min_variance=2.0)),  # config 4 shape: 256-bit
+    (64, np.uint8, 32, 256, dict(nxcorr_threshold=0.9, subpixel_step=0.2, min_variance=2.0)),
+    (9, np.uint8, 32, 200, dict(nxcorr_threshold=0.8, subpixel_step=0.3)),
+    (17, np.uint16, 32, 200, dict(nxcorr_threshold=0.8, subpixel_step=0.15, min_variance=4.0)),
+    (12, np.uint8, 32, 200, dict(nxcorr_threshold=0.7, mode_full=True, consistency=True, max_lr_diff=0)),
+    (2, np.uint8, 16, 100, dict(nxcorr_threshold=0.5, subpixel_step=0.5)),
+    (5, np.uint16, 16, 101, dict(nxcorr_threshold=0.5, min_variance=0.0)),
+]
+
+
+@pytest.mark.parametrize("n,dtype,rows,cols,kw", CASES)
+def test_match_float_parity(handle, oracles, n, dtype, rows, cols, kw):
+    left, right, _ = synth.make_stacks(n, 512, cols, dtype, seed=11 * n + cols, row0=128, rows=rows)
+    want_d, want_c = oracles.port.match(left, right, **kw)
+    disp, corr = handle.match(_cuda(left), _cuda(right), Config(**kw))
+    got_d = disp.cpu().numpy()
+    assert got_d.dtype == want_d.dtype
+    if want_d.dtype == np.int16:
+        assert np.array_equal(got_d, want_d)
+        assert corr is None
+        return
+    got_c = corr.cpu().numpy()
+    invalid_w = np.isnan(want_d) | (want_d == -32768)
+    invalid_g = np.isnan(got_d) | (got_d == -32768)
+    # pixels whose NXC sits within 1e-6 of the threshold may flip (north_star); none expected
+    edge = np.abs(np.nan_to_num(want_c, nan=9.0) - kw["nxcorr_threshold"]) < 1e-6
+    assert np.array_equal(invalid_g | edge, invalid_w | edge), "valid masks differ"
+    assert np.array_equal(np.isnan(got_c), np.isnan(want_c))
+    ok = ~np.isnan(want_c)
+    assert np.max(np.abs(got_c[ok] - want_c[ok]), initial=0) <= 1e-5
+    both = ~(invalid_w | invalid_g)
+    assert np.max(np.abs(got_d[both] - want_d[both]), initial=0) <= 1e-3
+    # stronger: the kernels follow the reference's operation order, so everything is identical
+    assert _same(got_c, want_c), f"corrmap: {(~np.isclose(got_c, want_c, rtol=0, atol=0, equal_nan=True)).sum()} differ"
+    assert _same(got_d, want_d)
+    assert both.mean() > 0.2 or n <= 5, "test scene should have valid matches"
+
+
+@pytest.mark.parametrize("n,dtype,rows,cols,kw", [c for c in CASES if c[4].get("nxcorr_threshold") is not None][:8])
+def test_match_double_parity(handle, oracles, n, dtype, rows, cols, kw):
+    left, right, _ = synth.make_stacks(n, 512, cols, dtype, seed=3 * n + cols, row0=64, rows=rows)
+    want_d, want_c = oracles.port.match(left, right, double=True, **kw)
+    disp, corr = handle.match(_cuda(left), _cuda(right), Config(double=True, **kw))
+    got_d, got_c = disp.cpu().numpy(), corr.cpu().numpy()
+    assert got_c.dtype == np.float64 and got_d.dtype == np.float32
+    invalid_w = np.isnan(want_d) | (want_d == -32768)
+    invalid_g = np.isnan(got_d) | (got_d == -32768)
+    assert np.array_equal(invalid_g, invalid_w)
+    assert np.array_equal(np.isnan(got_c), np.isnan(want_c))
+    ok = ~np.isnan(want_c)
+    assert np.max(np.abs(got_c[ok] - want_c[ok]), initial=0) <= 1e-12
+    both = ~invalid_w
+    assert np.max(np.abs(got_d[both] - want_d[both]), initial=0) <= 1e-3
+
+
+def test_match_against_unmodified_reference(handle, oracles):
+    """Same comparison, but against the compiled reference sources themselves (when they travelled)."""
+    if not oracles.ref.available():
+        pytest.skip("oracle/_ref/libbicos_ref.so not present")
+    left, right, _ = synth.make_stacks(33, 512, 400, np.uint8, seed=99, row0=256, rows=64)
+    for kw in (dict(nxcorr_threshold=0.96, min_variance=2.0),
+               dict(nxcorr_threshold=0.96, min_variance=2.0, subpixel_step=0.1, consistency=True, max_lr_diff=1)):
+        want_d, want_c = oracles.ref.match(left, right, **kw)
+        disp, corr = handle.match(_cuda(left), _cuda(right), Config(**kw))
+        assert _same(disp.cpu().numpy(), want_d)
+        assert _same(corr.cpu().numpy(), want_c)
+
+
+def test_match_host_and_rows(handle, oracles):
+    """Host-buffer entry point and the row-sharded entry point give the same answer."""
+    import torch
+
+    kw = dict(nxcorr_threshold=0.9, subpixel_step=0.1, consistency=True, max_lr_diff=1, min_variance=2.0)
+    left, right, _ = synth.make_stacks(33, 96, 256, np.uint8, seed=4)
+    want_d, want_c = oracles.port.match(left, right, **kw)
+    d, c = handle.match_host(left, right, Config(**kw))
+    assert _same(d, want_d) and _same(c, want_c)
+    l, r = _cuda(left), _cuda(right)
+    disp = torch.full((96, 256), 7.0, dtype=torch.float32, device="cuda")
+    corr = torch.full((96, 256), 7.0, dtype=torch.float32, device="cuda")
+    for rb, re in ((0, 31), (31, 64), (64, 96)):
+        handle.match(l, r, Config(**kw), out=(disp, corr), rows_range=(rb, re))
+    assert _same(disp.cpu().numpy(), want_d) and _same(corr.cpu().numpy(), want_c)
+
+
+def test_errors(handle):
+    import torch
+
+    import libbicos_b200 as lb
+
+    one = torch.zeros((1, 8, 8), dtype=torch.uint8, device="cuda")
+    with pytest.raises(lb.BicosError, match="at least two"):
+        handle.match(one, one, Config())
+    many = torch.zeros((20, 8, 8), dtype=torch.uint8, device="cuda")
+    with pytest.raises(lb.BicosError, match="363 bits"):
+        handle.match(many, many, Config(mode_full=True))
+    bad = torch.zeros((4, 8, 8), dtype=torch.float32, device="cuda")
+    with pytest.raises(lb.BicosError, match="depths"):
+        handle.match(bad, bad, Config())

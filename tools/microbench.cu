@@ -1,0 +1,114 @@
+// Pipe-throughput micro-benchmark for the search kernel's roofline denominator:
+// measures warp-instructions per clock per SM for POPC, LOP3, IMAD, VIMNMX, REDUX and
+// the mixes the Hamming search issues. Build: make -C tools. Run on the GPU box:
+//   tools/microbench > gpurun_out/microbench.txt
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); return 1; } } while (0)
+
+constexpr int CHAINS = 8;
+
+#define POPC(x) asm volatile("popc.b32 %0, %0;" : "+r"(x))
+#define LOP(x, y) asm volatile("lop3.b32 %0, %0, %1, %1, 0x96;" : "+r"(x) : "r"(y))
+#define IMAD(x, y) asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(x) : "r"(y))
+#define MINU(x, y) asm volatile("min.u32 %0, %0, %1;" : "+r"(x) : "r"(y))
+#define IADD(x, y) asm volatile("add.u32 %0, %0, %1;" : "+r"(x) : "r"(y))
+#define REDUX(x) asm volatile("redux.sync.min.u32 %0, %0, 0xffffffff;" : "+r"(x))
+#define SHFL(x) asm volatile("shfl.sync.bfly.b32 %0, %0, 1, 0x1f, 0xffffffff;" : "+r"(x))
+
+template<int MODE>
+__global__ void bench(uint32_t* out, long long* cycles, int iters, uint32_t seed) {
+    uint32_t x[CHAINS], y = seed | 3u;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c)
+        x[c] = seed * (c + 1) + threadIdx.x;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int c = 0; c < CHAINS; ++c) {
+            if (MODE == 0) { POPC(x[c]); }
+            if (MODE == 1) { LOP(x[c], y); }
+            if (MODE == 2) { IMAD(x[c], y); }
+            if (MODE == 3) { MINU(x[c], y); }
+            if (MODE == 4) { IADD(x[c], y); }
+            if (MODE == 5) { REDUX(x[c]); }
+            if (MODE == 6) { SHFL(x[c]); }
+            if (MODE == 7) { POPC(x[c]); LOP(x[c], y); }                       // 1 popc : 1 alu
+            if (MODE == 8) { POPC(x[c]); LOP(x[c], y); LOP(x[c], y); }          // 1 : 2
+            if (MODE == 9) { POPC(x[c]); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); } // 1 : 3
+            if (MODE == 10) { POPC(x[c]); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); } // 1 : 4
+            if (MODE == 11) { POPC(x[c]); IMAD(x[c], y); }                     // popc + fma pipe
+            if (MODE == 12) { POPC(x[c]); IMAD(x[c], y); LOP(x[c], y); LOP(x[c], y); } // 1 popc, 1 fma, 2 alu
+            if (MODE == 13) { POPC(x[c]); IMAD(x[c], y); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); } // 1,1,3
+            if (MODE == 14) { LOP(x[c], y); IMAD(x[c], y); }                   // alu + fma co-issue
+            if (MODE == 15) { POPC(x[c]); POPC(x[c]); POPC(x[c]); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); MINU(x[c], y); MINU(x[c], y); IMAD(x[c], y); IMAD(x[c], y); IMAD(x[c], y); } // search-like
+        }
+    }
+    const long long t1 = clock64();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c)
+        acc ^= x[c];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0)
+        cycles[blockIdx.x] = t1 - t0;
+}
+
+template<int MODE>
+int run(const char* name, int ops_per_chain_iter, int sms, uint32_t* out, long long* cyc) {
+    const int threads = 256, blocks_per_sm = 8, iters = 2048;
+    const int grid = sms * blocks_per_sm;
+    cudaEvent_t a, b;
+    CHECK(cudaEventCreate(&a));
+    CHECK(cudaEventCreate(&b));
+    bench<MODE><<<grid, threads>>>(out, cyc, 16, 1);
+    CHECK(cudaDeviceSynchronize());
+    CHECK(cudaEventRecord(a));
+    bench<MODE><<<grid, threads>>>(out, cyc, iters, 12345);
+    CHECK(cudaEventRecord(b));
+    CHECK(cudaDeviceSynchronize());
+    float ms = 0;
+    CHECK(cudaEventElapsedTime(&ms, a, b));
+    long long* h = new long long[grid];
+    CHECK(cudaMemcpy(h, cyc, sizeof(long long) * grid, cudaMemcpyDeviceToHost));
+    double avg = 0;
+    for (int i = 0; i < grid; ++i)
+        avg += (double)h[i];
+    avg /= grid;
+    delete[] h;
+    const double warp_instr_per_sm = (double)blocks_per_sm * (threads / 32) * iters * CHAINS * ops_per_chain_iter;
+    printf("%-28s %8.3f ms  %10.0f cyc/block  %6.3f warp-instr/clk/SM  (%5.2f thread-ops/clk/SM)  eff clock %.0f MHz\n",
+           name, ms, avg, warp_instr_per_sm / avg, 32.0 * warp_instr_per_sm / avg, avg / (ms * 1e3));
+    return 0;
+}
+
+int main() {
+    cudaDeviceProp p;
+    CHECK(cudaGetDeviceProperties(&p, 0));
+    printf("device %s, %d SMs, clock %.0f MHz\n", p.name, p.multiProcessorCount, p.clockRate / 1e3);
+    const int sms = p.multiProcessorCount;
+    uint32_t* out;
+    long long* cyc;
+    CHECK(cudaMalloc(&out, sizeof(uint32_t) * sms * 8 * 256));
+    CHECK(cudaMalloc(&cyc, sizeof(long long) * sms * 8));
+    run<0>("POPC", 1, sms, out, cyc);
+    run<1>("LOP3", 1, sms, out, cyc);
+    run<2>("IMAD", 1, sms, out, cyc);
+    run<3>("VIMNMX (min.u32)", 1, sms, out, cyc);
+    run<4>("IADD", 1, sms, out, cyc);
+    run<5>("REDUX.min", 1, sms, out, cyc);
+    run<6>("SHFL.bfly", 1, sms, out, cyc);
+    run<7>("POPC+1 LOP3", 2, sms, out, cyc);
+    run<8>("POPC+2 LOP3", 3, sms, out, cyc);
+    run<9>("POPC+3 LOP3", 4, sms, out, cyc);
+    run<10>("POPC+4 LOP3", 5, sms, out, cyc);
+    run<11>("POPC+IMAD", 2, sms, out, cyc);
+    run<12>("POPC+IMAD+2 LOP3", 4, sms, out, cyc);
+    run<13>("POPC+IMAD+3 LOP3", 5, sms, out, cyc);
+    run<14>("LOP3+IMAD", 2, sms, out, cyc);
+    run<15>("3POPC+6LOP+2MIN+3IMAD", 14, sms, out, cyc);
+    return 0;
+}
