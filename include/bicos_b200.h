@@ -141,6 +141,13 @@ int bicos_b200_match_rows(bicos_b200_handle h, const void* const* planes0,
 /* Blocks until all work enqueued through this handle's internal streams and `stream` is done. */
 int bicos_b200_synchronize(bicos_b200_handle h, void* stream);
 
+/* Per-stage device timing for benchmarks: while enabled, every match records CUDA events
+ * around its three stages (0 = both descriptor transforms, 1 = search, 2 = postfilter+refine)
+ * on the stream it runs on. bicos_b200_stage_times() waits for the device, then returns the
+ * accumulated milliseconds per stage and the number of matches they cover. */
+int bicos_b200_set_profiling(bicos_b200_handle h, int enabled);
+int bicos_b200_stage_times(bicos_b200_handle h, double* ms_out3, long long* matches_out);
+
 /* How many kernels of this library have been launched through the handle (bench bookkeeping). */
 long long bicos_b200_kernel_launches(bicos_b200_handle h);
 

@@ -24,7 +24,7 @@ EXPORTS = (
     "bicos_b200_descriptor_words", "bicos_b200_disparity_type", "bicos_b200_corrmap_type",
     "bicos_b200_transform", "bicos_b200_search", "bicos_b200_refine", "bicos_b200_match",
     "bicos_b200_match_host", "bicos_b200_match_rows", "bicos_b200_synchronize",
-    "bicos_b200_kernel_launches",
+    "bicos_b200_kernel_launches", "bicos_b200_set_profiling", "bicos_b200_stage_times",
 )
 
 
@@ -105,6 +105,8 @@ def lib():
         L.bicos_b200_match_rows.argtypes = [vp, pp, pp, i, i, i, sz, i, cfgp, i, i, vp, sz, vp, sz, vp]
         L.bicos_b200_match_host.argtypes = [vp, pp, pp, i, i, i, i, cfgp, vp, vp]
         L.bicos_b200_synchronize.argtypes = [vp, vp]
+        L.bicos_b200_set_profiling.argtypes = [vp, i]
+        L.bicos_b200_stage_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
         _lib = L
     return _lib
 
@@ -292,6 +294,17 @@ class Handle:
             n, rows, cols, depth, ctypes.byref(ccfg), disp.ctypes.data,
             corr.ctypes.data if corr is not None else None))
         return disp, corr
+
+    def set_profiling(self, enabled: bool) -> None:
+        """Record CUDA events around the three stages of every match (resets the accumulators)."""
+        _check(lib().bicos_b200_set_profiling(self._h, int(enabled)))
+
+    def stage_times(self):
+        """(ms_transform, ms_search, ms_refine) accumulated since set_profiling(True), and the match count."""
+        ms = (ctypes.c_double * 3)()
+        cnt = ctypes.c_longlong()
+        _check(lib().bicos_b200_stage_times(self._h, ms, ctypes.byref(cnt)))
+        return [float(v) for v in ms], int(cnt.value)
 
     def synchronize(self) -> None:
         _check(lib().bicos_b200_synchronize(self._h, self._stream()))

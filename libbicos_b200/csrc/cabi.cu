@@ -111,6 +111,9 @@ size_t depth_bytes(int depth) {
 
 } // namespace
 
+constexpr int MAX_BANDS = 8;
+constexpr int N_STAGES = 3; // transform (both stacks), search, refine
+
 struct bicos_b200_handle_s {
     int device = 0;
     DeviceBuffer desc0, desc1, fwd, rev_first, rev_last, xs;
@@ -118,6 +121,15 @@ struct bicos_b200_handle_s {
     float xs_step = -1.f;
     int xs_count = 0;
     long long launches = 0;
+    // host-buffer pipeline (bicos_b200_match_host): upload / compute / download streams
+    cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[MAX_BANDS] = {}, ev_done[MAX_BANDS] = {};
+    // optional per-stage timing (bicos_b200_set_profiling)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events; // N_STAGES + 1 events per recorded match
+    size_t prof_used = 0;
+    double stage_ms[N_STAGES] = { 0, 0, 0 };
+    long long stage_count = 0;
 };
 
 namespace {
@@ -177,6 +189,33 @@ int prepare_steps(bicos_b200_handle h, float step, cudaStream_t stream) {
     CU(cudaStreamSynchronize(stream)); // xs is a stack-owned pageable buffer
     h->xs_step = step;
     h->xs_count = (int)xs.size();
+    return 0;
+}
+
+int prof_mark(bicos_b200_handle h, cudaStream_t stream) {
+    if (!h->profiling)
+        return 0;
+    if (h->prof_used == h->prof_events.size()) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        h->prof_events.push_back(e);
+    }
+    CU(cudaEventRecord(h->prof_events[h->prof_used++], stream));
+    return 0;
+}
+
+// fold all completed (N_STAGES + 1)-event groups into stage_ms; requires the work to be finished
+int prof_collect(bicos_b200_handle h) {
+    const size_t group = N_STAGES + 1;
+    for (size_t g = 0; g + group <= h->prof_used; g += group) {
+        for (int st = 0; st < N_STAGES; ++st) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, h->prof_events[g + st], h->prof_events[g + st + 1]));
+            h->stage_ms[st] += ms;
+        }
+        h->stage_count += 1;
+    }
+    h->prof_used = 0;
     return 0;
 }
 
@@ -290,9 +329,13 @@ int do_match(
     uint32_t* d0 = static_cast<uint32_t*>(h->desc0.ptr);
     uint32_t* d1 = static_cast<uint32_t*>(h->desc1.ptr);
     const int is_u16 = depth == BICOS_B200_16U;
+    if (int rc = prof_mark(h, stream))
+        return rc;
     CU(launch_transform(t0, n, nrows, cols, pitch_bytes, is_u16, cfg->mode != 0, K, d0, dpw, stream));
     CU(launch_transform(t1, n, nrows, cols, pitch_bytes, is_u16, cfg->mode != 0, K, d1, dpw, stream));
     h->launches += 2;
+    if (int rc = prof_mark(h, stream))
+        return rc;
 
     uint32_t* rf = static_cast<uint32_t*>(h->rev_first.ptr);
     uint32_t* rl = static_cast<uint32_t*>(h->rev_last.ptr);
@@ -303,11 +346,15 @@ int do_match(
     }
     CU(launch_search(d0, d1, K, nrows, cols, dpw, flags, static_cast<int32_t*>(h->fwd.ptr), rf, rl, stream));
     h->launches += 1;
+    if (int rc = prof_mark(h, stream))
+        return rc;
 
     char* disp_rows = static_cast<char*>(disparity) + (size_t)row_begin * disparity_pitch;
     char* corr_rows = corrmap ? static_cast<char*>(corrmap) + (size_t)row_begin * corrmap_pitch : nullptr;
-    return do_refine(h, t0, t1, n, nrows, cols, pitch_bytes, depth, cfg, static_cast<int32_t*>(h->fwd.ptr), rf, rl,
-                     nullptr, disp_rows, disparity_pitch, corr_rows, corrmap_pitch, stream);
+    if (int rc = do_refine(h, t0, t1, n, nrows, cols, pitch_bytes, depth, cfg, static_cast<int32_t*>(h->fwd.ptr), rf, rl,
+                           nullptr, disp_rows, disparity_pitch, corr_rows, corrmap_pitch, stream))
+        return rc;
+    return prof_mark(h, stream);
 }
 
 } // namespace
@@ -358,6 +405,17 @@ int bicos_b200_destroy(bicos_b200_handle h) {
         cudaDeviceSynchronize();
         for (DeviceBuffer* b: { &h->desc0, &h->desc1, &h->fwd, &h->rev_first, &h->rev_last, &h->xs, &h->stage_in, &h->stage_disp, &h->stage_corr })
             b->release();
+        for (cudaEvent_t e: h->prof_events)
+            cudaEventDestroy(e);
+        for (int b = 0; b < MAX_BANDS; ++b) {
+            if (h->ev_in[b])
+                cudaEventDestroy(h->ev_in[b]);
+            if (h->ev_done[b])
+                cudaEventDestroy(h->ev_done[b]);
+        }
+        for (cudaStream_t st: { h->s_in, h->s_compute, h->s_out })
+            if (st)
+                cudaStreamDestroy(st);
     }
     delete h;
     return 0;
@@ -485,40 +543,120 @@ int bicos_b200_match_host(bicos_b200_handle h, const void* const* host_planes0,
         return fail(BICOS_B200_ERR_INVALID, "null argument");
     if (int rc = validate_common(n, rows, cols, depth, cfg, nullptr))
         return rc;
+    for (int i = 0; i < n; ++i)
+        if (!host_planes0[i] || !host_planes1[i])
+            return fail(BICOS_B200_ERR_INVALID, "image %d is null", i);
     DeviceGuard g(h->device);
-    cudaStream_t stream = nullptr;
+
+    // Rows are independent, so the image is cut into row bands that flow through three
+    // streams: band b+1 uploads while band b is matched and band b-1 downloads. With pinned
+    // host memory the copies are plain DMA; pageable memory still works (staged by the driver).
+    if (!h->s_in) {
+        CU(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+        for (int b = 0; b < MAX_BANDS; ++b) {
+            CU(cudaEventCreateWithFlags(&h->ev_in[b], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h->ev_done[b], cudaEventDisableTiming));
+        }
+    }
+    int bands = rows / 192;
+    bands = bands < 1 ? 1 : bands > MAX_BANDS ? MAX_BANDS : bands;
 
     const size_t eb = depth_bytes(depth);
     const size_t row_bytes = (size_t)cols * eb;
     const size_t pitch = (row_bytes + 15) & ~(size_t)15;
     const size_t plane_bytes = pitch * rows;
-    CU(h->stage_in.reserve(plane_bytes * 2 * n));
-    std::vector<const void*> dev0(n), dev1(n);
-    char* base = static_cast<char*>(h->stage_in.ptr);
-    for (int i = 0; i < n; ++i) {
-        if (!host_planes0[i] || !host_planes1[i])
-            return fail(BICOS_B200_ERR_INVALID, "image %d is null", i);
-        dev0[i] = base + plane_bytes * i;
-        dev1[i] = base + plane_bytes * (n + i);
-        CU(cudaMemcpy2DAsync(const_cast<void*>(dev0[i]), pitch, host_planes0[i], row_bytes, row_bytes, rows, cudaMemcpyHostToDevice, stream));
-        CU(cudaMemcpy2DAsync(const_cast<void*>(dev1[i]), pitch, host_planes1[i], row_bytes, row_bytes, rows, cudaMemcpyHostToDevice, stream));
-    }
-
     const size_t disp_eb = cfg->nxcorr_threshold >= 0 ? 4 : 2;
     const size_t corr_eb = cfg->precision != 0 ? 8 : 4;
     const bool want_corr = host_corrmap && cfg->nxcorr_threshold >= 0;
-    CU(h->stage_disp.reserve((size_t)rows * cols * disp_eb));
-    if (want_corr)
-        CU(h->stage_corr.reserve((size_t)rows * cols * corr_eb));
+    const int band_rows_max = (rows + bands - 1) / bands + 1;
+    {
+        // reserve everything up front: a reallocation inside the pipeline would stall it
+        int K = 0;
+        validate_common(n, rows, cols, depth, cfg, &K);
+        const size_t dpw = desc_pitch_for(cols, K);
+        const size_t px = (size_t)band_rows_max * cols;
+        CU(h->stage_in.reserve(plane_bytes * 2 * n));
+        CU(h->stage_disp.reserve((size_t)rows * cols * disp_eb));
+        if (want_corr)
+            CU(h->stage_corr.reserve((size_t)rows * cols * corr_eb));
+        CU(h->desc0.reserve(dpw * band_rows_max * sizeof(uint32_t)));
+        CU(h->desc1.reserve(dpw * band_rows_max * sizeof(uint32_t)));
+        CU(h->fwd.reserve(px * sizeof(int32_t)));
+        CU(h->rev_first.reserve(px * sizeof(uint32_t)));
+        CU(h->rev_last.reserve(px * sizeof(uint32_t)));
+        if (cfg->nxcorr_threshold >= 0 && cfg->subpixel_step >= 0)
+            if (int rc = prepare_steps(h, cfg->subpixel_step, h->s_compute))
+                return rc;
+    }
 
-    if (int rc = do_match(h, dev0.data(), dev1.data(), n, rows, cols, pitch, depth, cfg, 0, rows, h->stage_disp.ptr,
-                          (size_t)cols * disp_eb, want_corr ? h->stage_corr.ptr : nullptr, (size_t)cols * corr_eb, stream))
+    std::vector<const void*> dev0(n), dev1(n);
+    char* base = static_cast<char*>(h->stage_in.ptr);
+    for (int i = 0; i < n; ++i) {
+        dev0[i] = base + plane_bytes * i;
+        dev1[i] = base + plane_bytes * (n + i);
+    }
+
+    for (int b = 0; b < bands; ++b) {
+        const int rb = (int)((long long)rows * b / bands), re = (int)((long long)rows * (b + 1) / bands);
+        for (int i = 0; i < n; ++i) {
+            CU(cudaMemcpy2DAsync(const_cast<char*>(static_cast<const char*>(dev0[i])) + pitch * rb, pitch,
+                                 static_cast<const char*>(host_planes0[i]) + row_bytes * rb, row_bytes, row_bytes,
+                                 re - rb, cudaMemcpyHostToDevice, h->s_in));
+            CU(cudaMemcpy2DAsync(const_cast<char*>(static_cast<const char*>(dev1[i])) + pitch * rb, pitch,
+                                 static_cast<const char*>(host_planes1[i]) + row_bytes * rb, row_bytes, row_bytes,
+                                 re - rb, cudaMemcpyHostToDevice, h->s_in));
+        }
+        CU(cudaEventRecord(h->ev_in[b], h->s_in));
+    }
+    for (int b = 0; b < bands; ++b) {
+        const int rb = (int)((long long)rows * b / bands), re = (int)((long long)rows * (b + 1) / bands);
+        CU(cudaStreamWaitEvent(h->s_compute, h->ev_in[b], 0));
+        if (int rc = do_match(h, dev0.data(), dev1.data(), n, rows, cols, pitch, depth, cfg, rb, re, h->stage_disp.ptr,
+                              (size_t)cols * disp_eb, want_corr ? h->stage_corr.ptr : nullptr, (size_t)cols * corr_eb,
+                              h->s_compute)) {
+            cudaDeviceSynchronize();
+            return rc;
+        }
+        CU(cudaEventRecord(h->ev_done[b], h->s_compute));
+        CU(cudaStreamWaitEvent(h->s_out, h->ev_done[b], 0));
+        const size_t off = (size_t)rb * cols, cnt = (size_t)(re - rb) * cols;
+        CU(cudaMemcpyAsync(static_cast<char*>(host_disparity) + off * disp_eb,
+                           static_cast<char*>(h->stage_disp.ptr) + off * disp_eb, cnt * disp_eb,
+                           cudaMemcpyDeviceToHost, h->s_out));
+        if (want_corr)
+            CU(cudaMemcpyAsync(static_cast<char*>(host_corrmap) + off * corr_eb,
+                               static_cast<char*>(h->stage_corr.ptr) + off * corr_eb, cnt * corr_eb,
+                               cudaMemcpyDeviceToHost, h->s_out));
+    }
+    CU(cudaStreamSynchronize(h->s_out));
+    CU(cudaStreamSynchronize(h->s_compute));
+    return 0;
+}
+
+int bicos_b200_set_profiling(bicos_b200_handle h, int enabled) {
+    if (!h)
+        return fail(BICOS_B200_ERR_INVALID, "null handle");
+    h->profiling = enabled != 0;
+    h->prof_used = 0;
+    for (int st = 0; st < N_STAGES; ++st)
+        h->stage_ms[st] = 0;
+    h->stage_count = 0;
+    return 0;
+}
+
+int bicos_b200_stage_times(bicos_b200_handle h, double* ms_out, long long* matches_out) {
+    if (!h || !ms_out)
+        return fail(BICOS_B200_ERR_INVALID, "null argument");
+    DeviceGuard g(h->device);
+    CU(cudaDeviceSynchronize());
+    if (int rc = prof_collect(h))
         return rc;
-
-    CU(cudaMemcpyAsync(host_disparity, h->stage_disp.ptr, (size_t)rows * cols * disp_eb, cudaMemcpyDeviceToHost, stream));
-    if (want_corr)
-        CU(cudaMemcpyAsync(host_corrmap, h->stage_corr.ptr, (size_t)rows * cols * corr_eb, cudaMemcpyDeviceToHost, stream));
-    CU(cudaStreamSynchronize(stream));
+    for (int st = 0; st < N_STAGES; ++st)
+        ms_out[st] = h->stage_ms[st];
+    if (matches_out)
+        *matches_out = h->stage_count;
     return 0;
 }
 

@@ -93,42 +93,52 @@ __host__ __device__ constexpr int limited_base(int t) {
     return t < 2 ? 3 * t : 4 * t - 2;
 }
 
+// LIMITED descriptor of one pixel (descriptor_transform.hpp:31-73) without per-element
+// branches: the per-t bits are computed for every t up to the compile-time capacity at
+// compile-time positions (pixels past n are zero padding), the bits at and above the
+// runtime tail position are masked off, and the four tail bits -- which involve p[n-2],
+// p[n-1] and the pair sum two steps back -- are inserted at their runtime position.
 template<typename TIn, int K>
-__device__ __forceinline__ void describe_limited(const int (&p)[8 * K + 2], int n, Bits<K>& b) {
+__device__ __forceinline__ void describe_limited(
+    const int (&p)[8 * K + 2],
+    int n,
+    int ta, // p[n-2]
+    int tb, // p[n-1]
+    int tprev, // p[n-4] + p[n-3], or -1 when n < 4
+    Bits<K>& b
+) {
     constexpr int NB = 8 * K + 1; // largest n with 4n-7 <= 32K
     int sum = 0;
 #pragma unroll
     for (int t = 0; t < NB; ++t)
-        if (t < n)
-            sum += p[t];
+        sum += p[t]; // padding is zero
     b.clear();
 #pragma unroll
-    for (int t = 0; t < NB - 1; ++t) {
+    for (int t = 0; t < NB - 2; ++t) {
+        // descriptor_transform.hpp:45-60
         const int base = limited_base(t);
-        if (t + 2 < n) {
-            // descriptor_transform.hpp:45-60
-            const bool b0 = p[t] < p[t + 1];
-            const bool b1 = p[t] < p[t + 2];
-            const bool b2 = p[t] * n < sum;
-            b.w[(base + 0) / 32] |= (uint32_t)b0 << ((base + 0) % 32);
-            b.w[(base + 1) / 32] |= (uint32_t)b1 << ((base + 1) % 32);
-            b.w[(base + 2) / 32] |= (uint32_t)b2 << ((base + 2) % 32);
-            if (t >= 2) {
-                const bool b3 = p[t - 2 < 0 ? 0 : t - 2] + p[t - 1 < 0 ? 0 : t - 1] < p[t] + p[t + 1];
-                b.w[(base + 3) / 32] |= (uint32_t)b3 << ((base + 3) % 32);
-            }
-        } else if (t + 2 == n) {
-            // descriptor_transform.hpp:62-69: tail for a = p[n-2], b = p[n-1]
-            const bool b0 = p[t] < p[t + 1];
-            const bool b1 = p[t] * n < sum;
-            const bool b2 = p[t + 1] * n < sum;
-            // previous pair sum of the same parity, -1 when it does not exist (n < 4)
-            const bool b3 = t >= 2 ? (p[t - 2 < 0 ? 0 : t - 2] + p[t - 1 < 0 ? 0 : t - 1] < p[t] + p[t + 1]) : true;
-            b.w[(base + 0) / 32] |= (uint32_t)b0 << ((base + 0) % 32);
-            b.w[(base + 1) / 32] |= (uint32_t)b1 << ((base + 1) % 32);
-            b.w[(base + 2) / 32] |= (uint32_t)b2 << ((base + 2) % 32);
-            b.w[(base + 3) / 32] |= (uint32_t)b3 << ((base + 3) % 32);
-        }
+        b.w[(base + 0) / 32] |= (uint32_t)(p[t] < p[t + 1]) << ((base + 0) % 32);
+        b.w[(base + 1) / 32] |= (uint32_t)(p[t] < p[t + 2]) << ((base + 1) % 32);
+        b.w[(base + 2) / 32] |= (uint32_t)(p[t] * n < sum) << ((base + 2) % 32);
+        if (t >= 2)
+            b.w[(base + 3) / 32] |= (uint32_t)(p[t >= 2 ? t - 2 : 0] + p[t >= 1 ? t - 1 : 0] < p[t] + p[t + 1]) << ((base + 3) % 32);
+    }
+    // descriptor_transform.hpp:62-69: tail for a = p[n-2], b = p[n-1]
+    const int pos = n >= 4 ? 4 * n - 10 : 3 * (n - 2); // == limited_base(n - 2)
+    const uint32_t nib = (uint32_t)(ta < tb) | ((uint32_t)(ta * n < sum) << 1) | ((uint32_t)(tb * n < sum) << 2)
+        | ((uint32_t)(tprev < ta + tb) << 3);
+    const unsigned long long ins = (unsigned long long)nib << (pos & 31);
+    const int word = pos >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int keep = pos - 32 * k; // loop bits of this word that belong to t < n-2
+        const uint32_t mask = keep <= 0 ? 0u : keep >= 32 ? 0xFFFFFFFFu : ((1u << keep) - 1u);
+        uint32_t v = b.w[k] & mask;
+        if (k == word)
+            v |= (uint32_t)ins;
+        if (k == word + 1)
+            v |= (uint32_t)(ins >> 32);
+        b.w[k] = v;
     }
 }
 
@@ -194,6 +204,11 @@ __global__ void __launch_bounds__(THREADS) transform_limited_kernel(
 #pragma unroll
     for (int t = 0; t < NB; ++t)
         raw[t] = t < n ? load_group<TIn>(planes.p[t], row_off, col, cols, vec_ok != 0) : 0u;
+    // the planes the tail bits need, by runtime index (cache hits: just loaded above)
+    const uint32_t raw_a = load_group<TIn>(planes.p[n - 2], row_off, col, cols, vec_ok != 0);
+    const uint32_t raw_b = load_group<TIn>(planes.p[n - 1], row_off, col, cols, vec_ok != 0);
+    const uint32_t raw_pa = n >= 4 ? load_group<TIn>(planes.p[n - 4], row_off, col, cols, vec_ok != 0) : 0u;
+    const uint32_t raw_pb = n >= 4 ? load_group<TIn>(planes.p[n - 3], row_off, col, cols, vec_ok != 0) : 0u;
 
     uint32_t* out = desc + (size_t)row * desc_pitch_words + (size_t)col * K;
 #pragma unroll
@@ -204,8 +219,9 @@ __global__ void __launch_bounds__(THREADS) transform_limited_kernel(
             for (int t = 0; t < NB; ++t)
                 p[t] = Px<TIn>::get(raw[t], q);
             p[NB] = 0;
+            const int tprev = n >= 4 ? Px<TIn>::get(raw_pa, q) + Px<TIn>::get(raw_pb, q) : -1;
             Bits<K> b;
-            describe_limited<TIn, K>(p, n, b);
+            describe_limited<TIn, K>(p, n, Px<TIn>::get(raw_a, q), Px<TIn>::get(raw_b, q), tprev, b);
             store_desc<K>(out + q * K, b);
         }
     }
