@@ -263,6 +263,164 @@ __global__ void __launch_bounds__(THREADS) transform_full_kernel(
     }
 }
 
+// ---- uint8 LIMITED fast path: 4 pixels per register, byte-lane SIMD ---------------------
+//
+// ncu shows the scalar kernel above is ALU-bound (one compare + select + insert per bit per
+// pixel), not HBM-bound. Here the four adjacent pixels a thread loads as one 32-bit word stay
+// packed: an unsigned byte compare a < b of all four lanes is the carry out of b + ~a, i.e.
+// maj(b, ~a, carry into bit 7), two integer instructions given the pre-masked low 7 bits of
+// every plane word. Pair sums (9 bits) are compared in two 16-bit-lane words (even / odd
+// pixels). The mean test p*n < sum becomes p < ceil(sum/n), a byte compare against a
+// per-pixel threshold. Result bits are gathered "transposed": byte j of acc[m] holds
+// descriptor bits 8m..8m+7 of pixel j; a final byte permute yields the K words per pixel.
+// Runtime n: bits of t >= n-2 are masked off afterwards and the 4 tail bits are inserted at
+// their runtime position, exactly as in describe_limited().
+
+__device__ __forceinline__ uint32_t lt_u8x4(uint32_t a_nlo, uint32_t a, uint32_t b_lo, uint32_t b) {
+    // bit 7 of every byte: a < b. a_nlo = ~a & 0x7f.., b_lo = b & 0x7f..
+    uint32_t r;
+    const uint32_t t = b_lo + a_nlo; // per byte <= 254: no carry across lanes
+    asm("lop3.b32 %0, %1, %2, %3, 0xb2;" : "=r"(r) : "r"(b), "r"(a), "r"(t)); // maj(b, ~a, t)
+    return r;
+}
+
+template<int K>
+__global__ void __launch_bounds__(THREADS) transform_limited_u8x4_kernel(
+    const PlaneTable planes,
+    int n,
+    int cols,
+    size_t in_pitch,
+    uint32_t* __restrict__ desc,
+    size_t desc_pitch_words
+) {
+    constexpr int NB = 8 * K + 1;
+    constexpr uint32_t LO7 = 0x7F7F7F7Fu, H16 = 0x80008000u, B16 = 0x00FF00FFu;
+    const int row = blockIdx.y;
+    const int col = (blockIdx.x * THREADS + threadIdx.x) * 4;
+    if (col >= cols)
+        return;
+    const size_t row_off = (size_t)row * in_pitch + col;
+
+    uint32_t raw[NB + 1];
+#pragma unroll
+    for (int t = 0; t < NB; ++t)
+        raw[t] = t < n ? __ldg(reinterpret_cast<const uint32_t*>(static_cast<const char*>(planes.p[t]) + row_off)) : 0u;
+    raw[NB] = 0u;
+    const uint32_t ta = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const char*>(planes.p[n - 2]) + row_off));
+    const uint32_t tb = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const char*>(planes.p[n - 1]) + row_off));
+    uint32_t tpa = 0u, tpb = 0u;
+    if (n >= 4) {
+        tpa = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const char*>(planes.p[n - 4]) + row_off));
+        tpb = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const char*>(planes.p[n - 3]) + row_off));
+    }
+
+    // per-pixel sums in 16-bit lanes (even pixels 0,2 / odd pixels 1,3); padding planes are 0
+    uint32_t se = 0u, so = 0u;
+#pragma unroll
+    for (int t = 0; t < NB; ++t) {
+        se += raw[t] & B16;
+        so += (raw[t] >> 8) & B16;
+    }
+    // thr = ceil(sum / n) per pixel: p*n < sum  <=>  p < thr. Exact reciprocal multiply:
+    // floor(x/n) == (x*m) >> 24 with m = ceil(2^24/n) for x < 2^15, n <= 65.
+    const uint32_t m = ((1u << 24) + (uint32_t)n - 1u) / (uint32_t)n;
+    const uint32_t nm1 = (uint32_t)n - 1u;
+    const uint32_t q0 = (((se & 0xFFFFu) + nm1) * m) >> 24, q2 = (((se >> 16) + nm1) * m) >> 24;
+    const uint32_t q1 = (((so & 0xFFFFu) + nm1) * m) >> 24, q3 = (((so >> 16) + nm1) * m) >> 24;
+    const uint32_t thr = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+    const uint32_t thr_lo = thr & LO7;
+
+    uint32_t acc[4 * K];
+#pragma unroll
+    for (int i = 0; i < 4 * K; ++i)
+        acc[i] = 0u;
+
+    // bit7-of-each-byte result -> descriptor bit POS of the four pixels
+    auto put8 = [&](int pos, uint32_t r) {
+        const int sh = 7 - (pos & 7);
+        acc[pos >> 3] |= (r >> sh) & (0x01010101u << (pos & 7));
+    };
+    // 16-bit-lane results (bit15/31 CLEAR means "less"): even word -> bytes 0,2; odd -> bytes 1,3
+    auto put16 = [&](int pos, uint32_t de, uint32_t dod) {
+        acc[pos >> 3] |= (~de >> (15 - (pos & 7))) & (0x00010001u << (pos & 7));
+        acc[pos >> 3] |= (~dod >> (7 - (pos & 7))) & (0x01000100u << (pos & 7));
+    };
+
+    uint32_t lo_next = raw[0] & LO7, lo_next2 = raw[1] & LO7; // (b & 0x7f) of p[t+1], p[t+2]
+    uint32_t pe_prev2 = 0u, po_prev2 = 0u, pe_prev1 = 0u, po_prev1 = 0u; // ps(t-2), ps(t-1)
+    uint32_t e_cur = raw[0] & B16, o_cur = (raw[0] >> 8) & B16;
+#pragma unroll
+    for (int t = 0; t < NB - 2; ++t) {
+        const int base = limited_base(t);
+        const uint32_t a = raw[t], b = raw[t + 1], c = raw[t + 2];
+        const uint32_t a_lo = lo_next;
+        const uint32_t b_lo = lo_next2;
+        const uint32_t c_lo = c & LO7;
+        lo_next = b_lo;
+        lo_next2 = c_lo;
+        const uint32_t a_nlo = a_lo ^ LO7;
+        put8(base + 0, lt_u8x4(a_nlo, a, b_lo, b)); // p[t] < p[t+1]
+        put8(base + 1, lt_u8x4(a_nlo, a, c_lo, c)); // p[t] < p[t+2]
+        put8(base + 2, lt_u8x4(a_nlo, a, thr_lo, thr)); // p[t]*n < sum
+        const uint32_t e_nxt = b & B16, o_nxt = (b >> 8) & B16;
+        const uint32_t pe = e_cur + e_nxt, po = o_cur + o_nxt; // ps(t) in 16-bit lanes, <= 510
+        if (t >= 2) // ps(t-2) < ps(t): bit 15 of (x | 0x8000) - y stays set iff x >= y
+            put16(base + 3, (pe_prev2 | H16) - pe, (po_prev2 | H16) - po);
+        pe_prev2 = pe_prev1;
+        po_prev2 = po_prev1;
+        pe_prev1 = pe;
+        po_prev1 = po;
+        e_cur = e_nxt;
+        o_cur = o_nxt;
+    }
+
+    // tail bits (descriptor_transform.hpp:62-69), per pixel lanes
+    const uint32_t ta_nlo = (ta & LO7) ^ LO7;
+    const uint32_t r0 = lt_u8x4(ta_nlo, ta, tb & LO7, tb);
+    const uint32_t r1 = lt_u8x4(ta_nlo, ta, thr_lo, thr);
+    const uint32_t r2 = lt_u8x4((tb & LO7) ^ LO7, tb, thr_lo, thr);
+    const uint32_t ab_e = (ta & B16) + (tb & B16), ab_o = ((ta >> 8) & B16) + ((tb >> 8) & B16);
+    const uint32_t pv_e = (tpa & B16) + (tpb & B16), pv_o = ((tpa >> 8) & B16) + ((tpb >> 8) & B16);
+    // n < 4: the previous pair sum is -1, the bit is always set
+    const uint32_t r3e = n >= 4 ? ~((pv_e | H16) - ab_e) : 0xFFFFFFFFu;
+    const uint32_t r3o = n >= 4 ? ~((pv_o | H16) - ab_o) : 0xFFFFFFFFu;
+
+    const int pos = n >= 4 ? 4 * n - 10 : 3 * (n - 2); // == limited_base(n - 2)
+    const int word = pos >> 5;
+    uint32_t keep_mask[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int keep = pos - 32 * k;
+        keep_mask[k] = keep <= 0 ? 0u : keep >= 32 ? 0xFFFFFFFFu : ((1u << keep) - 1u);
+    }
+
+    uint32_t* out = desc + (size_t)row * desc_pitch_words + (size_t)col * K;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (col + j < cols) {
+            const int s16 = (j >> 1) * 16 + 15; // bit of the 16-bit-lane result of pixel j
+            const uint32_t r3 = (j & 1) ? r3o : r3e;
+            const uint32_t nib = ((r0 >> (8 * j + 7)) & 1u) | (((r1 >> (8 * j + 7)) & 1u) << 1)
+                | (((r2 >> (8 * j + 7)) & 1u) << 2) | (((r3 >> s16) & 1u) << 3);
+            const unsigned long long ins = (unsigned long long)nib << (pos & 31);
+            Bits<K> d;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                // bytes j of acc[4k .. 4k+3] -> word k of pixel j
+                const uint32_t lo = __byte_perm(acc[4 * k], acc[4 * k + 1], 0x0040 + 0x11 * j);
+                const uint32_t hi = __byte_perm(acc[4 * k + 2], acc[4 * k + 3], 0x0040 + 0x11 * j);
+                uint32_t v = __byte_perm(lo, hi, 0x5410) & keep_mask[k];
+                if (k == word)
+                    v |= (uint32_t)ins;
+                if (k == word + 1)
+                    v |= (uint32_t)(ins >> 32);
+                d.w[k] = v;
+            }
+            store_desc<K>(out + j * K, d);
+        }
+    }
+}
+
 constexpr int full_words(int n) {
     const int bits = n * n - 2 * n + 3;
     return bits <= 32 ? 1 : bits <= 64 ? 2 : bits <= 128 ? 4 : 8;
@@ -343,6 +501,12 @@ cudaError_t launch_limited_k(
     if (n > 8 * K + 1)
         return cudaErrorInvalidValue;
     const dim3 grid((cols + THREADS * PT - 1) / (THREADS * PT), rows);
+    if constexpr (sizeof(TIn) == 1) {
+        if (vec_ok) {
+            transform_limited_u8x4_kernel<K><<<grid, THREADS, 0, stream>>>(planes, n, cols, in_pitch, desc, desc_pitch_words);
+            return cudaGetLastError();
+        }
+    }
     transform_limited_kernel<TIn, K>
         <<<grid, THREADS, 0, stream>>>(planes, n, cols, in_pitch, vec_ok, desc, desc_pitch_words);
     return cudaGetLastError();
