@@ -295,18 +295,6 @@ def test_pybicos_drop_in(handle, oracles):
         pybicos.match([left[0]], [right[0]], cfg)
 
 
-def test_unmodified_reference_pybicos_on_our_backend(handle, oracles, tmp_path):
-    """The reference's own pybicos/__init__.py, untouched, driving our pybicos_c.so on the GPU."""
-    import os
-    import subprocess
-    import sys
-
-    ref_init = "/root/reference/pybicos/__init__.py"
-    if not os.path.exists(ref_init):
-        pytest.skip("reference checkout not present on the GPU box")
-    # (kept for completeness: the reference tree does not travel with gpurun)
-
-
 def test_full_size_properties(handle):
     """BASELINE sizes, where the oracle is too slow: size-independent properties of the path."""
     import torch
