@@ -183,3 +183,81 @@ class _Lib:
 
 ref = _Lib(os.path.join(_HERE, "_ref", "libbicos_ref.so"), "ref_", has_double=False)
 port = _Lib(os.path.join(_HERE, "libbicos_oracle.so"), "orc_", has_double=True)
+
+
+class _RefConfig(ctypes.Structure):
+    _fields_ = [("nxcorr_threshold", ctypes.c_float), ("subpixel_step", ctypes.c_float),
+                ("min_variance", ctypes.c_float), ("mode", ctypes.c_int), ("precision", ctypes.c_int),
+                ("variant_type", ctypes.c_int), ("max_lr_diff", ctypes.c_int), ("no_dupes", ctypes.c_int)]
+
+
+class _RefCuda:
+    """The UNMODIFIED reference CUDA backend (src/impl/cuda.cu), compiled for sm_100a against
+    oracle/shim by `make -C oracle refcuda` into oracle/_ref/libbicos_refcuda.so: the second
+    baseline ("the reference's own CUDA build on the same B200"). Needs a GPU to run; used by
+    bench.py / tools/bench_configs.py for timing and by one GPU test as a cross-check.
+
+    Its outputs follow the reference's CUDA conventions, which differ from the CPU oracle:
+    integer mode returns int16, corrmap cells that were never evaluated are uninitialised,
+    and nvcc contracts the interpolation polynomial into FMAs."""
+
+    def __init__(self, path):
+        self.path = path
+        self._lib = None
+
+    def available(self) -> bool:
+        return os.path.exists(self.path)
+
+    @property
+    def lib(self):
+        if self._lib is None:
+            if not self.available():
+                raise RuntimeError(f"{self.path} missing: run `make -C oracle refcuda`")
+            self._lib = ctypes.CDLL(self.path)
+            self._lib.refcuda_last_error.restype = ctypes.c_char_p
+        return self._lib
+
+    @staticmethod
+    def _cfg(nxcorr_threshold=0.5, subpixel_step=None, min_variance=None, mode_full=False,
+             consistency=False, max_lr_diff=1, no_dupes=False, double=False):
+        return _RefConfig(_opt(nxcorr_threshold), _opt(subpixel_step), _opt(min_variance), int(mode_full),
+                          int(double), int(consistency), int(max_lr_diff), int(no_dupes))
+
+    def match(self, stack0, stack1, **kw):
+        s0, s1 = _c(stack0), _c(stack1)
+        n, rows, cols = s0.shape
+        cfg = self._cfg(**kw)
+        disp_buf = np.empty((rows, cols), dtype=np.float32)
+        corr_buf = np.full((rows, cols), np.nan, dtype=np.float64)
+        dt, ct = ctypes.c_int(0), ctypes.c_int(0)
+        rc = self.lib.refcuda_match(_p(s0), _p(s1), ctypes.c_int(n), ctypes.c_int(rows), ctypes.c_int(cols),
+                                    ctypes.c_int(_depth(s0)), ctypes.byref(cfg), _p(disp_buf), ctypes.byref(dt),
+                                    _p(corr_buf), ctypes.byref(ct))
+        if rc != 0:
+            raise RuntimeError(self.lib.refcuda_last_error().decode())
+        if dt.value == CV_16S:
+            disp = disp_buf.view(np.int16).reshape(-1)[: rows * cols].reshape(rows, cols).copy()
+        else:
+            disp = disp_buf
+        corr = None
+        if ct.value == CV_32F:
+            corr = corr_buf.view(np.float32).reshape(-1)[: rows * cols].reshape(rows, cols).copy()
+        elif ct.value == CV_64F:
+            corr = corr_buf
+        return disp, corr
+
+    def time(self, stack0, stack1, warmup=3, iters=10, **kw) -> float:
+        """ms per BICOS::match, device-resident inputs, CUDA events around `iters` calls."""
+        s0, s1 = _c(stack0), _c(stack1)
+        n, rows, cols = s0.shape
+        cfg = self._cfg(**kw)
+        ms = ctypes.c_float(0)
+        rc = self.lib.refcuda_time(_p(s0), _p(s1), ctypes.c_int(n), ctypes.c_int(rows), ctypes.c_int(cols),
+                                   ctypes.c_int(_depth(s0)), ctypes.byref(cfg), ctypes.c_int(warmup),
+                                   ctypes.c_int(iters), ctypes.byref(ms))
+        if rc != 0:
+            raise RuntimeError(self.lib.refcuda_last_error().decode())
+        return float(ms.value)
+
+
+refcuda = _RefCuda(os.path.join(_HERE, "_ref", "libbicos_refcuda.so"))

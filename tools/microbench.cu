@@ -18,6 +18,14 @@ constexpr int CHAINS = 8;
 #define IADD(x, y) asm volatile("add.u32 %0, %0, %1;" : "+r"(x) : "r"(y))
 #define REDUX(x) asm volatile("redux.sync.min.u32 %0, %0, 0xffffffff;" : "+r"(x))
 #define SHFL(x) asm volatile("shfl.sync.bfly.b32 %0, %0, 1, 0x1f, 0xffffffff;" : "+r"(x))
+// floating-point / byte-permute ops of the refine kernel (values are bit patterns, not meaningful floats)
+#define FFMA(x, y) asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+r"(x) : "r"(y))
+#define FADD(x, y) asm volatile("add.rn.f32 %0, %0, %1;" : "+r"(x) : "r"(y))
+#define FFMA2(x, y) asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(x) : "l"(y))
+#define FMUL2(x, y) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(y))
+#define FADD2(x, y) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(y))
+#define PRMT(x, y) asm volatile("prmt.b32 %0, %0, %1, 0x5410;" : "+r"(x) : "r"(y))
+#define DP4A(x, y) asm volatile("dp4a.u32.u32 %0, %0, %1, %0;" : "+r"(x) : "r"(y))
 
 template<int MODE>
 __global__ void bench(uint32_t* out, long long* cycles, int iters, uint32_t seed) {
@@ -25,6 +33,10 @@ __global__ void bench(uint32_t* out, long long* cycles, int iters, uint32_t seed
 #pragma unroll
     for (int c = 0; c < CHAINS; ++c)
         x[c] = seed * (c + 1) + threadIdx.x;
+    unsigned long long x2[CHAINS], y2 = ((unsigned long long)(seed | 3u) << 32) | 0x3f800001u;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c)
+        x2[c] = ((unsigned long long)x[c] << 32) | x[c];
     __syncthreads();
     const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
@@ -45,6 +57,15 @@ __global__ void bench(uint32_t* out, long long* cycles, int iters, uint32_t seed
             if (MODE == 12) { POPC(x[c]); IMAD(x[c], y); LOP(x[c], y); LOP(x[c], y); } // 1 popc, 1 fma, 2 alu
             if (MODE == 13) { POPC(x[c]); IMAD(x[c], y); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); } // 1,1,3
             if (MODE == 14) { LOP(x[c], y); IMAD(x[c], y); }                   // alu + fma co-issue
+            if (MODE == 16) { FFMA(x[c], y); }
+            if (MODE == 17) { FADD(x[c], y); }
+            if (MODE == 18) { FFMA2(x2[c], y2); }
+            if (MODE == 19) { FMUL2(x2[c], y2); }
+            if (MODE == 20) { FADD2(x2[c], y2); }
+            if (MODE == 21) { PRMT(x[c], y); }
+            if (MODE == 22) { DP4A(x[c], y); }
+            if (MODE == 23) { FFMA2(x2[c], y2); LOP(x[c], y); }                 // packed fp32 + alu co-issue
+            if (MODE == 24) { FFMA(x[c], y); LOP(x[c], y); }
             if (MODE == 15) { POPC(x[c]); POPC(x[c]); POPC(x[c]); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); MINU(x[c], y); MINU(x[c], y); IMAD(x[c], y); IMAD(x[c], y); IMAD(x[c], y); } // search-like
         }
     }
@@ -52,7 +73,7 @@ __global__ void bench(uint32_t* out, long long* cycles, int iters, uint32_t seed
     uint32_t acc = 0;
 #pragma unroll
     for (int c = 0; c < CHAINS; ++c)
-        acc ^= x[c];
+        acc ^= x[c] ^ (uint32_t)x2[c] ^ (uint32_t)(x2[c] >> 32);
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
     if (threadIdx.x == 0)
         cycles[blockIdx.x] = t1 - t0;
@@ -137,5 +158,14 @@ int main(int argc, char** argv) {
     run<13>("POPC+IMAD+3 LOP3", 5, sms, out, cyc);
     run<14>("LOP3+IMAD", 2, sms, out, cyc);
     run<15>("3POPC+6LOP+2MIN+3IMAD", 14, sms, out, cyc);
+    run<16>("FFMA", 1, sms, out, cyc);
+    run<17>("FADD", 1, sms, out, cyc);
+    run<18>("FFMA2 (f32x2)", 1, sms, out, cyc);
+    run<19>("FMUL2 (f32x2)", 1, sms, out, cyc);
+    run<20>("FADD2 (f32x2)", 1, sms, out, cyc);
+    run<21>("PRMT", 1, sms, out, cyc);
+    run<22>("IDP4A", 1, sms, out, cyc);
+    run<23>("FFMA2+LOP3", 2, sms, out, cyc);
+    run<24>("FFMA+LOP3", 2, sms, out, cyc);
     return 0;
 }
