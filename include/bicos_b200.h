@@ -92,19 +92,23 @@ int bicos_b200_transform(bicos_b200_handle h, const void* const* planes, int n, 
                          size_t desc_pitch_words, void* stream);
 
 /* Stage 2+4a, reference bicos<>() search part (include/impl/cpu/bicos.hpp:50-76, 78-97).
- * fwd_best: device [rows][cols] int32 (best right column, -1 = no unique match).
- * rev_first / rev_last: device [rows][cols] uint32 column minima, needed for
- * FLAG_CONSISTENCY (rev_last only with FLAG_NODUPES as well); filled by this call. */
+ * All results are device [rows][cols] uint32 minima of keys cost << 16 | column, filled by
+ * this call:
+ *   fwd_first  per left pixel: lowest Hamming cost and the FIRST right column attaining it
+ *   fwd_last   (FLAG_NODUPES) same cost with 65535 - column: the LAST right column attaining
+ *              it; the match is unique iff both name the same column
+ *   rev_first / rev_last  (FLAG_CONSISTENCY; rev_last only with FLAG_NODUPES as well) the same
+ *              per right column over the left row: the reverse search of the consistency check */
 int bicos_b200_search(bicos_b200_handle h, const uint32_t* desc0, const uint32_t* desc1, int K,
-                      int rows, int cols, size_t desc_pitch_words, int flags, int32_t* fwd_best,
-                      uint32_t* rev_first, uint32_t* rev_last, void* stream);
+                      int rows, int cols, size_t desc_pitch_words, int flags, uint32_t* fwd_first,
+                      uint32_t* fwd_last, uint32_t* rev_first, uint32_t* rev_last, void* stream);
 
 /* Stage 4b+3, reference bicos<>() postfilter (bicos.hpp:95-110) + agree / agree_subpixel
- * (include/impl/cpu/agree.hpp:53-191). raw_disp_out (optional, dense int16 [rows][cols])
- * receives the postfilter result before the NXC test. */
+ * (include/impl/cpu/agree.hpp:53-191) on the keys of bicos_b200_search. raw_disp_out
+ * (optional, dense int16 [rows][cols]) receives the postfilter result before the NXC test. */
 int bicos_b200_refine(bicos_b200_handle h, const void* const* planes0, const void* const* planes1,
                       int n, int rows, int cols, size_t pitch_bytes, int depth,
-                      const bicos_b200_config* cfg, const int32_t* fwd_best,
+                      const bicos_b200_config* cfg, const uint32_t* fwd_first, const uint32_t* fwd_last,
                       const uint32_t* rev_first, const uint32_t* rev_last, int16_t* raw_disp_out,
                       void* disparity, size_t disparity_pitch_bytes, void* corrmap,
                       size_t corrmap_pitch_bytes, void* stream);
@@ -127,6 +131,16 @@ int bicos_b200_match(bicos_b200_handle h, const void* const* planes0, const void
 int bicos_b200_match_host(bicos_b200_handle h, const void* const* host_planes0,
                           const void* const* host_planes1, int n, int rows, int cols, int depth,
                           const bicos_b200_config* cfg, void* host_disparity, void* host_corrmap);
+
+/* The same in two halves, for callers that keep several frames in flight (one handle per
+ * frame in flight): _begin validates, enqueues all copies and kernels on the handle's own
+ * streams and returns; _end blocks until the host buffers hold the results. The host buffers
+ * must stay valid, and should be pinned, between the two calls. A second _begin on a handle
+ * whose previous host match has not been ended is an error. */
+int bicos_b200_match_host_begin(bicos_b200_handle h, const void* const* host_planes0,
+                                const void* const* host_planes1, int n, int rows, int cols, int depth,
+                                const bicos_b200_config* cfg, void* host_disparity, void* host_corrmap);
+int bicos_b200_match_host_end(bicos_b200_handle h);
 
 /* Row-sharded variant for one process driving several GPUs: rows [row_begin, row_end) of the
  * same device-resident inputs are matched on this handle's device and written into the

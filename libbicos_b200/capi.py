@@ -23,7 +23,7 @@ EXPORTS = (
     "bicos_b200_last_error", "bicos_b200_device_count", "bicos_b200_create", "bicos_b200_destroy",
     "bicos_b200_descriptor_words", "bicos_b200_disparity_type", "bicos_b200_corrmap_type",
     "bicos_b200_transform", "bicos_b200_search", "bicos_b200_refine", "bicos_b200_match",
-    "bicos_b200_match_host", "bicos_b200_match_rows", "bicos_b200_synchronize",
+    "bicos_b200_match_host", "bicos_b200_match_host_begin", "bicos_b200_match_host_end", "bicos_b200_match_rows", "bicos_b200_synchronize",
     "bicos_b200_kernel_launches", "bicos_b200_set_profiling", "bicos_b200_stage_times",
 )
 
@@ -99,11 +99,13 @@ def lib():
         L.bicos_b200_disparity_type.argtypes = [cfgp]
         L.bicos_b200_corrmap_type.argtypes = [cfgp]
         L.bicos_b200_transform.argtypes = [vp, pp, i, i, i, sz, i, i, vp, sz, vp]
-        L.bicos_b200_search.argtypes = [vp, vp, vp, i, i, i, sz, i, vp, vp, vp, vp]
-        L.bicos_b200_refine.argtypes = [vp, pp, pp, i, i, i, sz, i, cfgp, vp, vp, vp, vp, vp, sz, vp, sz, vp]
+        L.bicos_b200_search.argtypes = [vp, vp, vp, i, i, i, sz, i, vp, vp, vp, vp, vp]
+        L.bicos_b200_refine.argtypes = [vp, pp, pp, i, i, i, sz, i, cfgp, vp, vp, vp, vp, vp, vp, sz, vp, sz, vp]
         L.bicos_b200_match.argtypes = [vp, pp, pp, i, i, i, sz, i, cfgp, vp, sz, vp, sz, vp]
         L.bicos_b200_match_rows.argtypes = [vp, pp, pp, i, i, i, sz, i, cfgp, i, i, vp, sz, vp, sz, vp]
         L.bicos_b200_match_host.argtypes = [vp, pp, pp, i, i, i, i, cfgp, vp, vp]
+        L.bicos_b200_match_host_begin.argtypes = [vp, pp, pp, i, i, i, i, cfgp, vp, vp]
+        L.bicos_b200_match_host_end.argtypes = [vp]
         L.bicos_b200_synchronize.argtypes = [vp, vp]
         L.bicos_b200_set_profiling.argtypes = [vp, i]
         L.bicos_b200_stage_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
@@ -191,18 +193,26 @@ class Handle:
         return desc, k
 
     def search(self, desc0, desc1, k: int, cols: int, flags: int):
-        """Row-wise search on pitched descriptors -> (fwd_best, rev_first, rev_last) [rows, cols]."""
+        """Row-wise search on pitched descriptors -> (fwd_first, fwd_last, rev_first, rev_last).
+
+        Each is a [rows, cols] int32 tensor holding uint32 keys cost << 16 | column (see
+        include/bicos_b200.h), or None when `flags` does not need it."""
         import torch
 
         rows, pitch_words = desc0.shape
         dev = desc0.device
-        fwd = torch.empty((rows, cols), dtype=torch.int32, device=dev)
-        revf = torch.empty((rows, cols), dtype=torch.int32, device=dev) if flags & FLAG_CONSISTENCY else None
-        revl = torch.empty((rows, cols), dtype=torch.int32, device=dev) if flags == 3 else None
+
+        def keys(needed):
+            return torch.empty((rows, cols), dtype=torch.int32, device=dev) if needed else None
+
+        fwdf = keys(True)
+        fwdl = keys(flags & FLAG_NODUPES)
+        revf = keys(flags & FLAG_CONSISTENCY)
+        revl = keys(flags == (FLAG_NODUPES | FLAG_CONSISTENCY))
+        ptr = [t.data_ptr() if t is not None else None for t in (fwdf, fwdl, revf, revl)]
         _check(lib().bicos_b200_search(self._h, desc0.data_ptr(), desc1.data_ptr(), k, rows, cols, pitch_words,
-                                       flags, fwd.data_ptr(), revf.data_ptr() if revf is not None else None,
-                                       revl.data_ptr() if revl is not None else None, self._stream()))
-        return fwd, revf, revl
+                                       flags, *ptr, self._stream()))
+        return fwdf, fwdl, revf, revl
 
     def _outputs(self, cfg: Config, rows: int, cols: int, device):
         import torch
@@ -216,8 +226,9 @@ class Handle:
             corr = torch.empty((rows, cols), dtype=torch.float64 if ct == TYPE_64F else torch.float32, device=device)
         return ccfg, disp, corr
 
-    def refine(self, stack0, stack1, cfg: Config, fwd, revf=None, revl=None, want_raw: bool = True):
-        """Postfilter + NXC refinement -> (disparity, corrmap or None, raw int16 or None)."""
+    def refine(self, stack0, stack1, cfg: Config, keys, want_raw: bool = True):
+        """Postfilter + NXC refinement on the 4-tuple returned by search()
+        -> (disparity, corrmap or None, raw int16 or None)."""
         import torch
 
         p0, n, rows, cols, pitch, depth = self._stack_info(stack0)
@@ -227,8 +238,8 @@ class Handle:
         ccfg, disp, corr = self._outputs(cfg, rows, cols, stack0.device)
         raw = torch.empty((rows, cols), dtype=torch.int16, device=stack0.device) if want_raw else None
         _check(lib().bicos_b200_refine(
-            self._h, p0, p1, n, rows, cols, pitch, depth, ctypes.byref(ccfg), fwd.data_ptr(),
-            revf.data_ptr() if revf is not None else None, revl.data_ptr() if revl is not None else None,
+            self._h, p0, p1, n, rows, cols, pitch, depth, ctypes.byref(ccfg),
+            *[t.data_ptr() if t is not None else None for t in keys],
             raw.data_ptr() if raw is not None else None, disp.data_ptr(), disp.stride(0) * disp.element_size(),
             corr.data_ptr() if corr is not None else None,
             corr.stride(0) * corr.element_size() if corr is not None else 0, self._stream()))
@@ -262,6 +273,15 @@ class Handle:
 
     def match_host(self, stack0, stack1, cfg: Config, out=None):
         """Host-resident match on numpy arrays / CPU tensors [n, rows, cols]; H2D and D2H included."""
+        res = self.match_host_begin(stack0, stack1, cfg, out)
+        self.match_host_end()
+        return res
+
+    def match_host_begin(self, stack0, stack1, cfg: Config, out=None):
+        """Enqueue a host-resident match and return its (disparity, corrmap) buffers at once; they
+        hold the result only after match_host_end(). One match in flight per handle: keep several
+        frames in flight with several handles. The inputs must stay alive (and should be pinned)
+        until match_host_end()."""
         import numpy as np
 
         def as_np(a):
@@ -279,8 +299,10 @@ class Handle:
         else:
             raise BicosError("bad input depths, only uint8 and uint16 are supported")
         n, rows, cols = s0.shape
-        planes0 = [np.ascontiguousarray(s0[t]) for t in range(n)]
-        planes1 = [np.ascontiguousarray(s1[t]) for t in range(n)]
+        # C-contiguous stacks are passed as views (the library then uploads whole bands with one
+        # strided copy); anything else is made dense plane by plane
+        planes0 = [s0[t] if s0[t].flags.c_contiguous else np.ascontiguousarray(s0[t]) for t in range(n)]
+        planes1 = [s1[t] if s1[t].flags.c_contiguous else np.ascontiguousarray(s1[t]) for t in range(n)]
         ccfg = cfg.to_c()
         dt = lib().bicos_b200_disparity_type(ctypes.byref(ccfg))
         ct = lib().bicos_b200_corrmap_type(ctypes.byref(ccfg))
@@ -289,11 +311,16 @@ class Handle:
             corr = np.empty((rows, cols), dtype=np.float64 if ct == TYPE_64F else np.float32) if ct else None
         else:
             disp, corr = (as_np(o) if o is not None else None for o in out)
-        _check(lib().bicos_b200_match_host(
+        _check(lib().bicos_b200_match_host_begin(
             self._h, _ptr_array([p.ctypes.data for p in planes0]), _ptr_array([p.ctypes.data for p in planes1]),
             n, rows, cols, depth, ctypes.byref(ccfg), disp.ctypes.data,
             corr.ctypes.data if corr is not None else None))
+        self._host_keepalive = (s0, s1, planes0, planes1, disp, corr)
         return disp, corr
+
+    def match_host_end(self) -> None:
+        _check(lib().bicos_b200_match_host_end(self._h))
+        self._host_keepalive = None
 
     def set_profiling(self, enabled: bool) -> None:
         """Record CUDA events around the three stages of every match (resets the accumulators)."""

@@ -116,10 +116,11 @@ constexpr int N_STAGES = 3; // transform (both stacks), search, refine
 
 struct bicos_b200_handle_s {
     int device = 0;
-    DeviceBuffer desc0, desc1, fwd, rev_first, rev_last, xs;
+    DeviceBuffer desc0, desc1, keys, xs; // keys: up to four [rows][cols] uint32 search-key arrays
     DeviceBuffer stage_in, stage_disp, stage_corr;
     float xs_step = -1.f;
     int xs_count = 0;
+    bool host_pending = false; // between bicos_b200_match_host_begin and _end
     long long launches = 0;
     // host-buffer pipeline (bicos_b200_match_host): upload / compute / download streams
     cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
@@ -223,6 +224,32 @@ size_t desc_pitch_for(int cols, int K) {
     return ((size_t)cols * K + 3) & ~(size_t)3; // rows start 16 B aligned
 }
 
+constexpr size_t KEYS_HEADER = 16; // the search kernel's work counter sits in front of the key arrays
+
+int key_arrays(int flags) {
+    return 1 + ((flags & FLAG_NODUPES) ? 1 : 0) + ((flags & FLAG_CONSISTENCY) ? ((flags & FLAG_NODUPES) ? 2 : 1) : 0);
+}
+
+struct KeyArrays {
+    uint32_t *fwd_first, *fwd_last, *rev_first, *rev_last;
+};
+
+KeyArrays split_keys(uint32_t* base, size_t px, int flags) {
+    KeyArrays k { base, nullptr, nullptr, nullptr };
+    uint32_t* next = base + px;
+    if (flags & FLAG_NODUPES) {
+        k.fwd_last = next;
+        next += px;
+    }
+    if (flags & FLAG_CONSISTENCY) {
+        k.rev_first = next;
+        next += px;
+        if (flags & FLAG_NODUPES)
+            k.rev_last = next;
+    }
+    return k;
+}
+
 int do_refine(
     bicos_b200_handle h,
     const PlaneTable& t0,
@@ -233,7 +260,8 @@ int do_refine(
     size_t pitch_bytes,
     int depth,
     const bicos_b200_config* cfg,
-    const int32_t* fwd_best,
+    const uint32_t* fwd_first,
+    const uint32_t* fwd_last,
     const uint32_t* rev_first,
     const uint32_t* rev_last,
     int16_t* raw_out,
@@ -266,7 +294,9 @@ int do_refine(
         prm.nsteps = h->xs_count;
         prm.xs = static_cast<const float*>(h->xs.ptr);
     }
-    prm.fwd_best = fwd_best;
+    prm.nodupes_forward = (search_flags(cfg) & FLAG_NODUPES) != 0;
+    prm.fwd_first = fwd_first;
+    prm.fwd_last = fwd_last;
     prm.rev_first = rev_first;
     prm.rev_last = rev_last;
     prm.raw_out = raw_out;
@@ -319,12 +349,10 @@ int do_match(
     const size_t px = (size_t)nrows * cols;
     CU(h->desc0.reserve(dpw * nrows * sizeof(uint32_t)));
     CU(h->desc1.reserve(dpw * nrows * sizeof(uint32_t)));
-    CU(h->fwd.reserve(px * sizeof(int32_t)));
-    if (flags & FLAG_CONSISTENCY) {
-        CU(h->rev_first.reserve(px * sizeof(uint32_t)));
-        if (flags & FLAG_NODUPES)
-            CU(h->rev_last.reserve(px * sizeof(uint32_t)));
-    }
+    // key arrays, contiguous so that one memset initialises them: fwd_first, then fwd_last
+    // (NODUPES), rev_first (CONSISTENCY), rev_last (both)
+    const int n_keys = key_arrays(flags);
+    CU(h->keys.reserve(KEYS_HEADER + px * sizeof(uint32_t) * n_keys));
 
     uint32_t* d0 = static_cast<uint32_t*>(h->desc0.ptr);
     uint32_t* d1 = static_cast<uint32_t*>(h->desc1.ptr);
@@ -337,21 +365,17 @@ int do_match(
     if (int rc = prof_mark(h, stream))
         return rc;
 
-    uint32_t* rf = static_cast<uint32_t*>(h->rev_first.ptr);
-    uint32_t* rl = static_cast<uint32_t*>(h->rev_last.ptr);
-    if (flags & FLAG_CONSISTENCY) {
-        CU(cudaMemsetAsync(rf, 0xFF, px * sizeof(uint32_t), stream));
-        if (flags & FLAG_NODUPES)
-            CU(cudaMemsetAsync(rl, 0xFF, px * sizeof(uint32_t), stream));
-    }
-    CU(launch_search(d0, d1, K, nrows, cols, dpw, flags, static_cast<int32_t*>(h->fwd.ptr), rf, rl, stream));
+    KeyArrays ka = split_keys(reinterpret_cast<uint32_t*>(static_cast<char*>(h->keys.ptr) + KEYS_HEADER), px, flags);
+    CU(cudaMemsetAsync(h->keys.ptr, 0xFF, KEYS_HEADER + px * sizeof(uint32_t) * n_keys, stream)); // work counter + keys
+    CU(launch_search(d0, d1, K, nrows, cols, dpw, flags, static_cast<unsigned long long*>(h->keys.ptr), ka.fwd_first,
+                     ka.fwd_last, ka.rev_first, ka.rev_last, stream));
     h->launches += 1;
     if (int rc = prof_mark(h, stream))
         return rc;
 
     char* disp_rows = static_cast<char*>(disparity) + (size_t)row_begin * disparity_pitch;
     char* corr_rows = corrmap ? static_cast<char*>(corrmap) + (size_t)row_begin * corrmap_pitch : nullptr;
-    if (int rc = do_refine(h, t0, t1, n, nrows, cols, pitch_bytes, depth, cfg, static_cast<int32_t*>(h->fwd.ptr), rf, rl,
+    if (int rc = do_refine(h, t0, t1, n, nrows, cols, pitch_bytes, depth, cfg, ka.fwd_first, ka.fwd_last, ka.rev_first, ka.rev_last,
                            nullptr, disp_rows, disparity_pitch, corr_rows, corrmap_pitch, stream))
         return rc;
     return prof_mark(h, stream);
@@ -403,7 +427,7 @@ int bicos_b200_destroy(bicos_b200_handle h) {
     {
         DeviceGuard g(h->device);
         cudaDeviceSynchronize();
-        for (DeviceBuffer* b: { &h->desc0, &h->desc1, &h->fwd, &h->rev_first, &h->rev_last, &h->xs, &h->stage_in, &h->stage_disp, &h->stage_corr })
+        for (DeviceBuffer* b: { &h->desc0, &h->desc1, &h->keys, &h->xs, &h->stage_in, &h->stage_disp, &h->stage_corr })
             b->release();
         for (cudaEvent_t e: h->prof_events)
             cudaEventDestroy(e);
@@ -464,9 +488,9 @@ int bicos_b200_transform(bicos_b200_handle h, const void* const* planes, int n, 
 }
 
 int bicos_b200_search(bicos_b200_handle h, const uint32_t* desc0, const uint32_t* desc1, int K,
-                      int rows, int cols, size_t desc_pitch_words, int flags, int32_t* fwd_best,
-                      uint32_t* rev_first, uint32_t* rev_last, void* stream) {
-    if (!h || !desc0 || !desc1 || !fwd_best)
+                      int rows, int cols, size_t desc_pitch_words, int flags, uint32_t* fwd_first,
+                      uint32_t* fwd_last, uint32_t* rev_first, uint32_t* rev_last, void* stream) {
+    if (!h || !desc0 || !desc1 || !fwd_first)
         return fail(BICOS_B200_ERR_INVALID, "null argument");
     if (K != 1 && K != 2 && K != 4 && K != 8)
         return fail(BICOS_B200_ERR_INVALID, "K must be 1, 2, 4 or 8");
@@ -474,33 +498,43 @@ int bicos_b200_search(bicos_b200_handle h, const uint32_t* desc0, const uint32_t
         return fail(BICOS_B200_ERR_INVALID, "bad flags");
     if (rows <= 0 || cols <= 0 || cols > 32767)
         return fail(BICOS_B200_ERR_INVALID, "bad image size");
+    if ((flags & FLAG_NODUPES) && !fwd_last)
+        return fail(BICOS_B200_ERR_INVALID, "no-duplicates search needs fwd_last");
     if ((flags & FLAG_CONSISTENCY) && (!rev_first || ((flags & FLAG_NODUPES) && !rev_last)))
         return fail(BICOS_B200_ERR_INVALID, "consistency search needs rev_first (and rev_last with no_dupes)");
     if (desc_pitch_words < (size_t)cols * K || (desc_pitch_words % 4) != 0)
         return fail(BICOS_B200_ERR_INVALID, "descriptor rows must be 16-byte aligned and hold cols*K words");
     DeviceGuard g(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const size_t px = (size_t)rows * cols;
+    const size_t bytes = (size_t)rows * cols * sizeof(uint32_t);
+    CU(h->keys.reserve(KEYS_HEADER));
+    CU(cudaMemsetAsync(h->keys.ptr, 0xFF, KEYS_HEADER, s)); // work counter
+    CU(cudaMemsetAsync(fwd_first, 0xFF, bytes, s));
+    if (flags & FLAG_NODUPES)
+        CU(cudaMemsetAsync(fwd_last, 0xFF, bytes, s));
     if (flags & FLAG_CONSISTENCY) {
-        CU(cudaMemsetAsync(rev_first, 0xFF, px * sizeof(uint32_t), s));
+        CU(cudaMemsetAsync(rev_first, 0xFF, bytes, s));
         if (flags & FLAG_NODUPES)
-            CU(cudaMemsetAsync(rev_last, 0xFF, px * sizeof(uint32_t), s));
+            CU(cudaMemsetAsync(rev_last, 0xFF, bytes, s));
     }
-    CU(launch_search(desc0, desc1, K, rows, cols, desc_pitch_words, flags, fwd_best, rev_first, rev_last, s));
+    CU(launch_search(desc0, desc1, K, rows, cols, desc_pitch_words, flags, static_cast<unsigned long long*>(h->keys.ptr),
+                     fwd_first, fwd_last, rev_first, rev_last, s));
     h->launches += 1;
     return 0;
 }
 
 int bicos_b200_refine(bicos_b200_handle h, const void* const* planes0, const void* const* planes1,
                       int n, int rows, int cols, size_t pitch_bytes, int depth,
-                      const bicos_b200_config* cfg, const int32_t* fwd_best,
+                      const bicos_b200_config* cfg, const uint32_t* fwd_first, const uint32_t* fwd_last,
                       const uint32_t* rev_first, const uint32_t* rev_last, int16_t* raw_disp_out,
                       void* disparity, size_t disparity_pitch_bytes, void* corrmap,
                       size_t corrmap_pitch_bytes, void* stream) {
-    if (!h || !planes0 || !planes1 || !fwd_best || !disparity)
+    if (!h || !planes0 || !planes1 || !fwd_first || !disparity)
         return fail(BICOS_B200_ERR_INVALID, "null argument");
     if (int rc = validate_common(n, rows, cols, depth, cfg, nullptr))
         return rc;
+    if ((search_flags(cfg) & FLAG_NODUPES) && !fwd_last)
+        return fail(BICOS_B200_ERR_INVALID, "no-duplicates postfilter needs fwd_last");
     if (cfg->variant_type != 0 && (!rev_first || (cfg->no_dupes && !rev_last)))
         return fail(BICOS_B200_ERR_INVALID, "consistency postfilter needs rev_first (and rev_last with no_dupes)");
     DeviceGuard g(h->device);
@@ -509,8 +543,9 @@ int bicos_b200_refine(bicos_b200_handle h, const void* const* planes0, const voi
         return rc;
     if (int rc = fill_table(t1, planes1, n, 0))
         return rc;
-    return do_refine(h, t0, t1, n, rows, cols, pitch_bytes, depth, cfg, fwd_best, rev_first, rev_last, raw_disp_out,
-                     disparity, disparity_pitch_bytes, corrmap, corrmap_pitch_bytes, static_cast<cudaStream_t>(stream));
+    return do_refine(h, t0, t1, n, rows, cols, pitch_bytes, depth, cfg, fwd_first, fwd_last, rev_first, rev_last,
+                     raw_disp_out, disparity, disparity_pitch_bytes, corrmap, corrmap_pitch_bytes,
+                     static_cast<cudaStream_t>(stream));
 }
 
 int bicos_b200_match(bicos_b200_handle h, const void* const* planes0, const void* const* planes1,
@@ -536,11 +571,44 @@ int bicos_b200_match_rows(bicos_b200_handle h, const void* const* planes0,
                     disparity_pitch_bytes, corrmap, corrmap_pitch_bytes, static_cast<cudaStream_t>(stream));
 }
 
-int bicos_b200_match_host(bicos_b200_handle h, const void* const* host_planes0,
-                          const void* const* host_planes1, int n, int rows, int cols, int depth,
-                          const bicos_b200_config* cfg, void* host_disparity, void* host_corrmap) {
+// dense host planes that lie back to back in one allocation ([n][rows][cols], e.g. one numpy
+// array) can be uploaded band-wise with one strided 3-D copy instead of n 2-D copies
+static bool planes_contiguous(const void* const* planes, int n, size_t plane_bytes) {
+    for (int i = 1; i < n; ++i)
+        if (static_cast<const char*>(planes[i]) != static_cast<const char*>(planes[0]) + plane_bytes * i)
+            return false;
+    return true;
+}
+
+static cudaError_t upload_band(const void* const* host_planes, bool contiguous, char* dev_base, int n, int rows,
+                               size_t row_bytes, size_t pitch, int rb, int re, cudaStream_t stream) {
+    if (contiguous) {
+        cudaMemcpy3DParms p {};
+        p.srcPtr = make_cudaPitchedPtr(const_cast<void*>(host_planes[0]), row_bytes, row_bytes, (size_t)rows);
+        p.srcPos = make_cudaPos(0, (size_t)rb, 0);
+        p.dstPtr = make_cudaPitchedPtr(dev_base, pitch, row_bytes, (size_t)rows);
+        p.dstPos = make_cudaPos(0, (size_t)rb, 0);
+        p.extent = make_cudaExtent(row_bytes, (size_t)(re - rb), (size_t)n);
+        p.kind = cudaMemcpyHostToDevice;
+        return cudaMemcpy3DAsync(&p, stream);
+    }
+    for (int i = 0; i < n; ++i) {
+        cudaError_t err = cudaMemcpy2DAsync(dev_base + pitch * rows * i + pitch * rb, pitch,
+                                            static_cast<const char*>(host_planes[i]) + row_bytes * rb, row_bytes,
+                                            row_bytes, (size_t)(re - rb), cudaMemcpyHostToDevice, stream);
+        if (err != cudaSuccess)
+            return err;
+    }
+    return cudaSuccess;
+}
+
+int bicos_b200_match_host_begin(bicos_b200_handle h, const void* const* host_planes0,
+                                const void* const* host_planes1, int n, int rows, int cols, int depth,
+                                const bicos_b200_config* cfg, void* host_disparity, void* host_corrmap) {
     if (!h || !host_planes0 || !host_planes1 || !host_disparity)
         return fail(BICOS_B200_ERR_INVALID, "null argument");
+    if (h->host_pending)
+        return fail(BICOS_B200_ERR_INVALID, "a host match is already in flight on this handle: call bicos_b200_match_host_end first");
     if (int rc = validate_common(n, rows, cols, depth, cfg, nullptr))
         return rc;
     for (int i = 0; i < n; ++i)
@@ -583,9 +651,7 @@ int bicos_b200_match_host(bicos_b200_handle h, const void* const* host_planes0,
             CU(h->stage_corr.reserve((size_t)rows * cols * corr_eb));
         CU(h->desc0.reserve(dpw * band_rows_max * sizeof(uint32_t)));
         CU(h->desc1.reserve(dpw * band_rows_max * sizeof(uint32_t)));
-        CU(h->fwd.reserve(px * sizeof(int32_t)));
-        CU(h->rev_first.reserve(px * sizeof(uint32_t)));
-        CU(h->rev_last.reserve(px * sizeof(uint32_t)));
+        CU(h->keys.reserve(KEYS_HEADER + px * sizeof(uint32_t) * 4));
         if (cfg->nxcorr_threshold >= 0 && cfg->subpixel_step >= 0)
             if (int rc = prepare_steps(h, cfg->subpixel_step, h->s_compute))
                 return rc;
@@ -597,42 +663,64 @@ int bicos_b200_match_host(bicos_b200_handle h, const void* const* host_planes0,
         dev0[i] = base + plane_bytes * i;
         dev1[i] = base + plane_bytes * (n + i);
     }
+    const bool contig0 = planes_contiguous(host_planes0, n, row_bytes * rows);
+    const bool contig1 = planes_contiguous(host_planes1, n, row_bytes * rows);
 
-    for (int b = 0; b < bands; ++b) {
-        const int rb = (int)((long long)rows * b / bands), re = (int)((long long)rows * (b + 1) / bands);
-        for (int i = 0; i < n; ++i) {
-            CU(cudaMemcpy2DAsync(const_cast<char*>(static_cast<const char*>(dev0[i])) + pitch * rb, pitch,
-                                 static_cast<const char*>(host_planes0[i]) + row_bytes * rb, row_bytes, row_bytes,
-                                 re - rb, cudaMemcpyHostToDevice, h->s_in));
-            CU(cudaMemcpy2DAsync(const_cast<char*>(static_cast<const char*>(dev1[i])) + pitch * rb, pitch,
-                                 static_cast<const char*>(host_planes1[i]) + row_bytes * rb, row_bytes, row_bytes,
-                                 re - rb, cudaMemcpyHostToDevice, h->s_in));
-        }
-        CU(cudaEventRecord(h->ev_in[b], h->s_in));
-    }
-    for (int b = 0; b < bands; ++b) {
-        const int rb = (int)((long long)rows * b / bands), re = (int)((long long)rows * (b + 1) / bands);
-        CU(cudaStreamWaitEvent(h->s_compute, h->ev_in[b], 0));
-        if (int rc = do_match(h, dev0.data(), dev1.data(), n, rows, cols, pitch, depth, cfg, rb, re, h->stage_disp.ptr,
-                              (size_t)cols * disp_eb, want_corr ? h->stage_corr.ptr : nullptr, (size_t)cols * corr_eb,
-                              h->s_compute)) {
-            cudaDeviceSynchronize();
-            return rc;
-        }
-        CU(cudaEventRecord(h->ev_done[b], h->s_compute));
-        CU(cudaStreamWaitEvent(h->s_out, h->ev_done[b], 0));
-        const size_t off = (size_t)rb * cols, cnt = (size_t)(re - rb) * cols;
-        CU(cudaMemcpyAsync(static_cast<char*>(host_disparity) + off * disp_eb,
-                           static_cast<char*>(h->stage_disp.ptr) + off * disp_eb, cnt * disp_eb,
-                           cudaMemcpyDeviceToHost, h->s_out));
-        if (want_corr)
-            CU(cudaMemcpyAsync(static_cast<char*>(host_corrmap) + off * corr_eb,
-                               static_cast<char*>(h->stage_corr.ptr) + off * corr_eb, cnt * corr_eb,
+    // upload of band b is enqueued right before the match of band b, so the host never runs
+    // far ahead of the device with copy submissions while kernels wait to be launched
+    auto enqueue = [&]() -> int {
+        for (int b = 0; b < bands; ++b) {
+            const int rb = (int)((long long)rows * b / bands), re = (int)((long long)rows * (b + 1) / bands);
+            CU(upload_band(host_planes0, contig0, base, n, rows, row_bytes, pitch, rb, re, h->s_in));
+            CU(upload_band(host_planes1, contig1, base + plane_bytes * n, n, rows, row_bytes, pitch, rb, re, h->s_in));
+            CU(cudaEventRecord(h->ev_in[b], h->s_in));
+            CU(cudaStreamWaitEvent(h->s_compute, h->ev_in[b], 0));
+            if (int rc = do_match(h, dev0.data(), dev1.data(), n, rows, cols, pitch, depth, cfg, rb, re,
+                                  h->stage_disp.ptr, (size_t)cols * disp_eb, want_corr ? h->stage_corr.ptr : nullptr,
+                                  (size_t)cols * corr_eb, h->s_compute))
+                return rc;
+            CU(cudaEventRecord(h->ev_done[b], h->s_compute));
+            CU(cudaStreamWaitEvent(h->s_out, h->ev_done[b], 0));
+            const size_t off = (size_t)rb * cols, cnt = (size_t)(re - rb) * cols;
+            CU(cudaMemcpyAsync(static_cast<char*>(host_disparity) + off * disp_eb,
+                               static_cast<char*>(h->stage_disp.ptr) + off * disp_eb, cnt * disp_eb,
                                cudaMemcpyDeviceToHost, h->s_out));
+            if (want_corr)
+                CU(cudaMemcpyAsync(static_cast<char*>(host_corrmap) + off * corr_eb,
+                                   static_cast<char*>(h->stage_corr.ptr) + off * corr_eb, cnt * corr_eb,
+                                   cudaMemcpyDeviceToHost, h->s_out));
+        }
+        return 0;
+    };
+    if (int rc = enqueue()) {
+        const std::string keep = g_error;
+        cudaDeviceSynchronize(); // nothing of a half-enqueued match may still touch the host buffers
+        g_error = keep;
+        return rc;
     }
+    h->host_pending = true;
+    return 0;
+}
+
+int bicos_b200_match_host_end(bicos_b200_handle h) {
+    if (!h)
+        return fail(BICOS_B200_ERR_INVALID, "null handle");
+    if (!h->host_pending)
+        return 0;
+    DeviceGuard g(h->device);
+    h->host_pending = false;
     CU(cudaStreamSynchronize(h->s_out));
     CU(cudaStreamSynchronize(h->s_compute));
     return 0;
+}
+
+int bicos_b200_match_host(bicos_b200_handle h, const void* const* host_planes0,
+                          const void* const* host_planes1, int n, int rows, int cols, int depth,
+                          const bicos_b200_config* cfg, void* host_disparity, void* host_corrmap) {
+    if (int rc = bicos_b200_match_host_begin(h, host_planes0, host_planes1, n, rows, cols, depth, cfg, host_disparity,
+                                             host_corrmap))
+        return rc;
+    return bicos_b200_match_host_end(h);
 }
 
 int bicos_b200_set_profiling(bicos_b200_handle h, int enabled) {

@@ -7,9 +7,11 @@
 //                  passed as a by-value table of plane pointers (no host-mapped tables)
 //   descriptors    [rows][desc_pitch_words] uint32, K = 1/2/4/8 words per pixel,
 //                  bit i of a descriptor = bit i%32 of word i/32; rows start 16 B aligned
-//   search result  fwd_best [rows][cols] int32: best right column or -1 (no unique match)
-//                  rev_first/rev_last [rows][cols] uint32 keys (cost<<16 | col0) resp.
-//                  (cost<<16 | 65535-col0): column-wise minima for the consistency check
+//   search result  four [rows][cols] uint32 key arrays, all minima of cost<<16 | column:
+//                  fwd_first (cost<<16 | col1) / fwd_last (cost<<16 | 65535-col1): per left
+//                  pixel, first and last right column attaining the minimal cost;
+//                  rev_first (cost<<16 | col0) / rev_last (cost<<16 | 65535-col0): the same per
+//                  right column over the left row, for the consistency check
 //   outputs        disparity int16 or float32, corrmap float32 or float64, both pitched
 #pragma once
 
@@ -42,7 +44,9 @@ struct RefineParams {
     int subpixel;
     int nsteps; // number of x values of the float loop x=-1; x<=1; x+=step
     const float* xs; // device array [nsteps] with exactly those float values
-    const int32_t* fwd_best;
+    int nodupes_forward; // forward search must be unique: compare fwd_first with fwd_last
+    const uint32_t* fwd_first;
+    const uint32_t* fwd_last;
     const uint32_t* rev_first;
     const uint32_t* rev_last;
     int16_t* raw_out; // optional [rows][cols] dense: postfilter result before the NXC test
@@ -69,7 +73,9 @@ cudaError_t launch_transform(
 
 // kernel 2: row-wise Hamming argmin, forward (per left pixel) and, with
 // FLAG_CONSISTENCY, the column-wise minima of the same W x W cost tile (reference a5/a6/a7).
-// rev_first / rev_last must be pre-filled with KEY_NONE by the caller.
+// All key arrays in use must be pre-filled with KEY_NONE by the caller (fwd_last / rev_last
+// are only touched with FLAG_NODUPES, rev_* only with FLAG_CONSISTENCY), and *work_counter
+// (the persistent grid's work queue) with all-ones: one memset of 0xFF covers both.
 cudaError_t launch_search(
     const uint32_t* desc0,
     const uint32_t* desc1,
@@ -78,7 +84,9 @@ cudaError_t launch_search(
     int cols,
     size_t desc_pitch_words,
     int flags,
-    int32_t* fwd_best,
+    unsigned long long* work_counter,
+    uint32_t* fwd_first,
+    uint32_t* fwd_last,
     uint32_t* rev_first,
     uint32_t* rev_last,
     cudaStream_t stream

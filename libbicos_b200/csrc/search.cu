@@ -4,9 +4,16 @@
 //   reference include/impl/cpu/bicos.hpp:29-76   ham / bicos_search
 //   reference include/impl/cuda/bicos.cuh:50-176 bicos_search / bicos_kernel[_smem]
 //
-// One CTA = one work unit = (image row, block of UNIT left pixels). Each thread keeps A
-// left descriptors in registers and scans the whole right row, which is staged through
-// shared memory in chunks and read with warp-uniform (broadcast) vector loads.
+// Work = rows x units x columns: a unit is a block of 128*A left pixels of one row, whose
+// descriptors a CTA keeps in registers (A per thread) while the right row streams through
+// shared memory in chunks, read with warp-uniform (broadcast) vector loads. The grid is
+// persistent -- (resident CTAs per SM) x (SM count) CTAs -- and the CTAs draw contiguous ranges
+// of (row, unit, column) steps from one atomic counter, each draw 1/(2G) of what is left
+// (guided self-scheduling), so that all SMs finish together whatever the image size: a
+// one-CTA-per-unit grid lost 8 % to the last partial wave at 2048x1536, and a static equal
+// split loses as much because the warp schedulers do not serve co-resident CTAs evenly. A unit
+// whose column range is split between CTAs is merged with atomicMin; A is chosen per image
+// width so that units tile the row with the least padding (1280 and 1920 columns: A = 5).
 //
 // Exactness without the reference's serial scan:
 //  * key = cost << 16 | column. min(key) over any partition of the row is the lowest cost
@@ -15,12 +22,13 @@
 //  * NODUPES (bicos.hpp:62-71: any later tie with the final minimum invalidates): a second
 //    key cost << 16 | (65535 - column) finds the LAST column with the minimal cost; a
 //    duplicate exists iff first != last. Both are plain min-reductions, so they merge
-//    associatively across lanes, chunks and CTAs.
+//    associatively across lanes, chunks and CTAs. The comparison itself happens in the
+//    postfilter (refine.cu), which reads both keys.
 //  * CONSISTENCY (bicos.hpp:99-106 runs a second full search from the matched right pixel
 //    over the left row): Hamming distance is symmetric, so the same W x W cost tile feeds the
 //    column-wise minima. Each warp min-reduces its 32*A costs for the current right column
 //    with REDUX and merges into a per-CTA shared array, which is flushed to global memory
-//    with atomicMin. The postfilter (refine.cu) then only looks up rev[best_col1].
+//    with atomicMin. The postfilter then only looks up rev[best_col1].
 //
 // Popcount pipe is the bound (16 POPC/clk/SM): carry-save compression brings a 128-bit
 // distance from 4 to 3 POPC and a 256-bit distance from 8 to 4 POPC.
@@ -31,9 +39,9 @@ namespace bicos_b200 {
 namespace {
 
 constexpr int THREADS = 128;
-constexpr int A = 4; // left descriptors per thread
-constexpr int UNIT = THREADS * A; // left pixels per CTA
 constexpr int CHUNK_BYTES = 16 * 1024; // right-row descriptor bytes staged per pass
+constexpr int STEP_ALIGN = 8; // CTA shares start on multiples of 8 columns (16 B aligned staging for every K)
+constexpr int MIN_TAKE = 256; // smallest range a CTA draws from the work counter (columns of one unit)
 
 __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
@@ -101,7 +109,7 @@ __device__ __forceinline__ uint32_t hamming(const Desc<K>& l, const Desc<K>& r) 
     }
 }
 
-template<int K, int FLAGS>
+template<int K, int FLAGS, int A>
 __global__ void __launch_bounds__(THREADS) search_kernel(
     const uint32_t* __restrict__ desc0,
     const uint32_t* __restrict__ desc1,
@@ -109,12 +117,17 @@ __global__ void __launch_bounds__(THREADS) search_kernel(
     size_t pitch_words,
     int chunk, // right descriptors staged per pass
     int units_per_row,
-    int32_t* __restrict__ fwd_best,
+    int steps_per_unit, // cols rounded up to STEP_ALIGN
+    long long total_steps, // rows * units_per_row * steps_per_unit
+    unsigned long long* __restrict__ work_counter, // steps handed out so far, minus one (starts at ~0)
+    uint32_t* __restrict__ fwd_first,
+    uint32_t* __restrict__ fwd_last,
     uint32_t* __restrict__ rev_first,
     uint32_t* __restrict__ rev_last
 ) {
     constexpr bool NODUPES = (FLAGS & FLAG_NODUPES) != 0;
     constexpr bool REVERSE = (FLAGS & FLAG_CONSISTENCY) != 0;
+    constexpr int UNIT = THREADS * A; // left pixels per unit
 
     extern __shared__ uint4 smem_raw[];
     uint32_t* const s_right = reinterpret_cast<uint32_t*>(smem_raw);
@@ -123,100 +136,138 @@ __global__ void __launch_bounds__(THREADS) search_kernel(
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int row = blockIdx.x / units_per_row;
-    const int unit = blockIdx.x - row * units_per_row;
 
-    const uint32_t* const row0 = desc0 + (size_t)row * pitch_words;
-    const uint32_t* const row1 = desc1 + (size_t)row * pitch_words;
+    __shared__ long long s_range[2];
+    const long long G = gridDim.x;
 
-    Desc<K> l[A];
-    uint32_t icol[A], icol_rev[A];
-    uint32_t mf[A], ml[A];
-#pragma unroll
-    for (int a = 0; a < A; ++a) {
-        const int i = unit * UNIT + a * THREADS + tid;
-        const bool valid = i < cols;
-        l[a] = load_desc<K>(row0 + (size_t)(valid ? i : cols - 1) * K);
-        // lanes past the end of the row carry bit 31 so that they never win a column minimum
-        icol[a] = valid ? (uint32_t)i : (0x80000000u | (uint32_t)i);
-        icol_rev[a] = valid ? (uint32_t)(65535 - i) : (0x80000000u | (uint32_t)i);
-        mf[a] = KEY_NONE;
-        ml[a] = KEY_NONE;
+    for (;;) {
+    // ---- draw the next range of steps: half of an equal share of what is left ------------------
+    __syncthreads(); // everyone is done with the previous range (and with s_range)
+    if (tid == 0) {
+        const long long handed_out = (long long)(*reinterpret_cast<volatile unsigned long long*>(work_counter) + 1ULL);
+        long long take = (total_steps - handed_out) / (2 * G);
+        take = (take < MIN_TAKE ? MIN_TAKE : take) & ~(long long)(STEP_ALIGN - 1);
+        const long long first = (long long)(atomicAdd(work_counter, (unsigned long long)take) + 1ULL);
+        s_range[0] = first;
+        s_range[1] = min(total_steps, first + take);
     }
+    __syncthreads();
+    long long s = s_range[0];
+    const long long s_end = s_range[1];
+    if (s >= total_steps)
+        break;
 
-    for (int j0 = 0; j0 < cols; j0 += chunk) {
-        const int cnt = min(chunk, cols - j0);
-        __syncthreads(); // previous chunk fully consumed and flushed
+    while (s < s_end) {
+        const long long ru = s / steps_per_unit;
+        const int jb = (int)(s - ru * steps_per_unit);
+        const int je = (int)min((long long)steps_per_unit, jb + (s_end - s));
+        s += je - jb;
+        const int j_end = min(je, cols);
+        if (jb >= j_end)
+            continue; // only the alignment padding of this unit was left
+        const int row = (int)(ru / units_per_row);
+        const int unit = (int)(ru - (long long)row * units_per_row);
+        const bool whole = jb == 0 && je == steps_per_unit; // no other CTA works on this unit
 
-        // stage the right descriptors [j0, j0+cnt) (rows are 16 B aligned and padded)
-        {
-            const uint4* src = reinterpret_cast<const uint4*>(row1 + (size_t)j0 * K);
-            const int nvec = (cnt * K + 3) / 4;
-            for (int v = tid; v < nvec; v += THREADS)
-                smem_raw[v] = src[v];
-            if constexpr (REVERSE) {
-                for (int v = tid; v < cnt; v += THREADS) {
-                    s_colf[v] = KEY_NONE;
-                    if constexpr (NODUPES)
-                        s_coll[v] = KEY_NONE;
+        const uint32_t* const row0 = desc0 + (size_t)row * pitch_words;
+        const uint32_t* const row1 = desc1 + (size_t)row * pitch_words;
+
+        Desc<K> l[A];
+        uint32_t icol[A], icol_rev[A];
+        uint32_t mf[A], ml[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            const int i = unit * UNIT + a * THREADS + tid;
+            const bool valid = i < cols;
+            l[a] = load_desc<K>(row0 + (size_t)(valid ? i : cols - 1) * K);
+            // lanes past the end of the row carry bit 31 so that they never win a column minimum
+            icol[a] = valid ? (uint32_t)i : (0x80000000u | (uint32_t)i);
+            icol_rev[a] = valid ? (uint32_t)(65535 - i) : (0x80000000u | (uint32_t)i);
+            mf[a] = KEY_NONE;
+            ml[a] = KEY_NONE;
+        }
+
+        for (int j0 = jb; j0 < j_end; j0 += chunk) {
+            const int cnt = min(chunk, j_end - j0);
+            __syncthreads(); // previous chunk fully consumed and flushed
+
+            // stage the right descriptors [j0, j0+cnt) (rows are 16 B aligned and padded)
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(row1 + (size_t)j0 * K);
+                const int nvec = (cnt * K + 3) / 4;
+                for (int v = tid; v < nvec; v += THREADS)
+                    smem_raw[v] = src[v];
+                if constexpr (REVERSE) {
+                    for (int v = tid; v < cnt; v += THREADS) {
+                        s_colf[v] = KEY_NONE;
+                        if constexpr (NODUPES)
+                            s_coll[v] = KEY_NONE;
+                    }
                 }
             }
-        }
-        __syncthreads();
+            __syncthreads();
 
 #pragma unroll 2
-        for (int jj = 0; jj < cnt; ++jj) {
-            const Desc<K> r = load_desc<K>(s_right + (size_t)jj * K); // warp-uniform: broadcast
-            const uint32_t j = (uint32_t)(j0 + jj);
-            const uint32_t jrev = 65535u - j;
-            uint32_t ck = KEY_NONE, ckl = KEY_NONE;
+            for (int jj = 0; jj < cnt; ++jj) {
+                const Desc<K> r = load_desc<K>(s_right + (size_t)jj * K); // warp-uniform: broadcast
+                const uint32_t j = (uint32_t)(j0 + jj);
+                const uint32_t jrev = 65535u - j;
+                uint32_t ck = KEY_NONE, ckl = KEY_NONE;
 #pragma unroll
-            for (int a = 0; a < A; ++a) {
-                const uint32_t cost16 = hamming<K>(l[a], r) << 16;
-                mf[a] = min(mf[a], cost16 + j);
-                if constexpr (NODUPES)
-                    ml[a] = min(ml[a], cost16 + jrev);
+                for (int a = 0; a < A; ++a) {
+                    const uint32_t cost16 = hamming<K>(l[a], r) << 16;
+                    mf[a] = min(mf[a], cost16 + j);
+                    if constexpr (NODUPES)
+                        ml[a] = min(ml[a], cost16 + jrev);
+                    if constexpr (REVERSE) {
+                        ck = min(ck, cost16 + icol[a]);
+                        if constexpr (NODUPES)
+                            ckl = min(ckl, cost16 + icol_rev[a]);
+                    }
+                }
                 if constexpr (REVERSE) {
-                    ck = min(ck, cost16 + icol[a]);
+                    ck = __reduce_min_sync(0xFFFFFFFFu, ck);
                     if constexpr (NODUPES)
-                        ckl = min(ckl, cost16 + icol_rev[a]);
+                        ckl = __reduce_min_sync(0xFFFFFFFFu, ckl);
+                    if (lane == 0) {
+                        atomicMin(&s_colf[jj], ck);
+                        if constexpr (NODUPES)
+                            atomicMin(&s_coll[jj], ckl);
+                    }
                 }
             }
+
             if constexpr (REVERSE) {
-                ck = __reduce_min_sync(0xFFFFFFFFu, ck);
-                if constexpr (NODUPES)
-                    ckl = __reduce_min_sync(0xFFFFFFFFu, ckl);
-                if (lane == 0) {
-                    atomicMin(&s_colf[jj], ck);
+                __syncthreads();
+                uint32_t* const gf = rev_first + (size_t)row * cols + j0;
+                uint32_t* const gl = rev_last + (size_t)row * cols + j0;
+                for (int v = tid; v < cnt; v += THREADS) {
+                    atomicMin(gf + v, s_colf[v]);
                     if constexpr (NODUPES)
-                        atomicMin(&s_coll[jj], ckl);
+                        atomicMin(gl + v, s_coll[v]);
                 }
             }
         }
 
-        if constexpr (REVERSE) {
-            __syncthreads();
-            uint32_t* const gf = rev_first + (size_t)row * cols + j0;
-            uint32_t* const gl = rev_last + (size_t)row * cols + j0;
-            for (int v = tid; v < cnt; v += THREADS) {
-                atomicMin(gf + v, s_colf[v]);
-                if constexpr (NODUPES)
-                    atomicMin(gl + v, s_coll[v]);
+        // forward keys of this unit; the postfilter decodes them (and compares first / last)
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            const int i = unit * UNIT + a * THREADS + tid;
+            if (i < cols) {
+                const size_t at = (size_t)row * cols + i;
+                if (whole) {
+                    fwd_first[at] = mf[a];
+                    if constexpr (NODUPES)
+                        fwd_last[at] = ml[a];
+                } else {
+                    atomicMin(fwd_first + at, mf[a]);
+                    if constexpr (NODUPES)
+                        atomicMin(fwd_last + at, ml[a]);
+                }
             }
         }
     }
-
-#pragma unroll
-    for (int a = 0; a < A; ++a) {
-        const int i = unit * UNIT + a * THREADS + tid;
-        if (i < cols) {
-            int best = (int)(mf[a] & 0xFFFFu);
-            if constexpr (NODUPES)
-                if ((ml[a] & 0xFFFFu) != 65535u - (uint32_t)best)
-                    best = -1; // at least two columns attain the minimum
-            fwd_best[(size_t)row * cols + i] = best;
-        }
-    }
+    } // next draw
 }
 
 int chunk_for(int K, int cols) {
@@ -225,43 +276,110 @@ int chunk_for(int K, int cols) {
     return padded < cap ? padded : cap;
 }
 
-template<int K, int FLAGS>
+// left descriptors per thread: the unit width 128*A that tiles `cols` with the least padding
+int pick_a(int cols) {
+    int best_a = 4;
+    long long best_pad = -1;
+    for (int a: { 4, 5, 3 }) {
+        const long long unit = (long long)THREADS * a;
+        const long long padded = (cols + unit - 1) / unit * unit;
+        if (best_pad < 0 || padded < best_pad) {
+            best_pad = padded;
+            best_a = a;
+        }
+    }
+    return best_a;
+}
+
+int sm_count() {
+    static thread_local int cached_dev = -1, cached_sms = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess)
+        return 148;
+    if (dev != cached_dev) {
+        if (cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            cached_sms = 148;
+        cached_dev = dev;
+    }
+    return cached_sms;
+}
+
+template<int K, int FLAGS, int A>
 cudaError_t launch_one(
     const uint32_t* desc0,
     const uint32_t* desc1,
     int rows,
     int cols,
     size_t pitch_words,
-    int32_t* fwd_best,
+    unsigned long long* work_counter,
+    uint32_t* fwd_first,
+    uint32_t* fwd_last,
     uint32_t* rev_first,
     uint32_t* rev_last,
     cudaStream_t stream
 ) {
     const int chunk = chunk_for(K, cols);
     const int smem = search_smem_bytes(K, cols, FLAGS);
-    cudaError_t err = cudaFuncSetAttribute(
-        search_kernel<K, FLAGS>,
-        cudaFuncAttributeMaxDynamicSharedMemorySize,
-        smem
-    );
+    auto kernel = search_kernel<K, FLAGS, A>;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess)
         return err;
-    const int units_per_row = (cols + UNIT - 1) / UNIT;
-    const long long grid = (long long)rows * units_per_row;
-    if (grid <= 0 || grid > 0x7FFFFFFFLL)
+    int occ = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, THREADS, smem);
+    if (err != cudaSuccess)
+        return err;
+    if (occ < 1)
         return cudaErrorInvalidConfiguration;
-    search_kernel<K, FLAGS><<<(unsigned)grid, THREADS, smem, stream>>>(
+    const int unit = THREADS * A;
+    const int units_per_row = (cols + unit - 1) / unit;
+    const int steps_per_unit = (cols + STEP_ALIGN - 1) / STEP_ALIGN * STEP_ALIGN;
+    const long long total = (long long)rows * units_per_row * steps_per_unit;
+    long long grid = (long long)sm_count() * occ;
+    const long long most = (total + 2 * MIN_TAKE - 1) / (2 * MIN_TAKE); // tiny images: fewer CTAs
+    if (grid > most)
+        grid = most;
+    if (grid < 1)
+        grid = 1;
+    kernel<<<(unsigned)grid, THREADS, smem, stream>>>(
         desc0,
         desc1,
         cols,
         pitch_words,
         chunk,
         units_per_row,
-        fwd_best,
+        steps_per_unit,
+        total,
+        work_counter,
+        fwd_first,
+        fwd_last,
         rev_first,
         rev_last
     );
     return cudaGetLastError();
+}
+
+template<int K, int FLAGS>
+cudaError_t launch_a(
+    const uint32_t* desc0,
+    const uint32_t* desc1,
+    int rows,
+    int cols,
+    size_t pitch_words,
+    unsigned long long* work_counter,
+    uint32_t* fwd_first,
+    uint32_t* fwd_last,
+    uint32_t* rev_first,
+    uint32_t* rev_last,
+    cudaStream_t stream
+) {
+    switch (pick_a(cols)) {
+        case 3:
+            return launch_one<K, FLAGS, 3>(desc0, desc1, rows, cols, pitch_words, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
+        case 5:
+            return launch_one<K, FLAGS, 5>(desc0, desc1, rows, cols, pitch_words, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
+        default:
+            return launch_one<K, FLAGS, 4>(desc0, desc1, rows, cols, pitch_words, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
+    }
 }
 
 template<int K>
@@ -272,20 +390,22 @@ cudaError_t launch_k(
     int cols,
     size_t pitch_words,
     int flags,
-    int32_t* fwd_best,
+    unsigned long long* work_counter,
+    uint32_t* fwd_first,
+    uint32_t* fwd_last,
     uint32_t* rev_first,
     uint32_t* rev_last,
     cudaStream_t stream
 ) {
     switch (flags) {
         case FLAG_NODUPES:
-            return launch_one<K, FLAG_NODUPES>(desc0, desc1, rows, cols, pitch_words, fwd_best, rev_first, rev_last, stream);
+            return launch_a<K, FLAG_NODUPES>(desc0, desc1, rows, cols, pitch_words, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
         case FLAG_CONSISTENCY:
-            return launch_one<K, FLAG_CONSISTENCY>(desc0, desc1, rows, cols, pitch_words, fwd_best, rev_first, rev_last, stream);
+            return launch_a<K, FLAG_CONSISTENCY>(desc0, desc1, rows, cols, pitch_words, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
         case FLAG_NODUPES | FLAG_CONSISTENCY:
-            return launch_one<K, FLAG_NODUPES | FLAG_CONSISTENCY>(desc0, desc1, rows, cols, pitch_words, fwd_best, rev_first, rev_last, stream);
+            return launch_a<K, FLAG_NODUPES | FLAG_CONSISTENCY>(desc0, desc1, rows, cols, pitch_words, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
         case 0: // plain first-minimum search (building block, not reachable from Config)
-            return launch_one<K, 0>(desc0, desc1, rows, cols, pitch_words, fwd_best, rev_first, rev_last, stream);
+            return launch_a<K, 0>(desc0, desc1, rows, cols, pitch_words, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
     }
     return cudaErrorInvalidValue;
 }
@@ -308,7 +428,9 @@ cudaError_t launch_search(
     int cols,
     size_t desc_pitch_words,
     int flags,
-    int32_t* fwd_best,
+    unsigned long long* work_counter,
+    uint32_t* fwd_first,
+    uint32_t* fwd_last,
     uint32_t* rev_first,
     uint32_t* rev_last,
     cudaStream_t stream
@@ -317,13 +439,13 @@ cudaError_t launch_search(
         return cudaErrorInvalidValue;
     switch (K) {
         case 1:
-            return launch_k<1>(desc0, desc1, rows, cols, desc_pitch_words, flags, fwd_best, rev_first, rev_last, stream);
+            return launch_k<1>(desc0, desc1, rows, cols, desc_pitch_words, flags, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
         case 2:
-            return launch_k<2>(desc0, desc1, rows, cols, desc_pitch_words, flags, fwd_best, rev_first, rev_last, stream);
+            return launch_k<2>(desc0, desc1, rows, cols, desc_pitch_words, flags, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
         case 4:
-            return launch_k<4>(desc0, desc1, rows, cols, desc_pitch_words, flags, fwd_best, rev_first, rev_last, stream);
+            return launch_k<4>(desc0, desc1, rows, cols, desc_pitch_words, flags, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
         case 8:
-            return launch_k<8>(desc0, desc1, rows, cols, desc_pitch_words, flags, fwd_best, rev_first, rev_last, stream);
+            return launch_k<8>(desc0, desc1, rows, cols, desc_pitch_words, flags, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
     }
     return cudaErrorInvalidValue;
 }

@@ -107,12 +107,12 @@ def test_search_postfilter_bit_exact(handle, oracles, k, flags, cols, bits):
         buf[:, : cols * k] = d.reshape(rows, cols * k)
         return torch.from_numpy(buf.view(np.int32)).cuda()
 
-    fwd, revf, revl = handle.search(pitched(d0), pitched(d1), k, cols, flags)
+    keys = handle.search(pitched(d0), pitched(d1), k, cols, flags)
     # postfilter only (threshold unset): the int16 disparity of reference bicos()
     dummy = torch.zeros((2, rows, cols), dtype=torch.uint8, device="cuda")
     cfg = Config(nxcorr_threshold=None, consistency=bool(flags & FLAG_CONSISTENCY), max_lr_diff=max_lr,
                  no_dupes=flags == 3)
-    disp, corr, raw = handle.refine(dummy, dummy, cfg, fwd, revf, revl)
+    disp, corr, raw = handle.refine(dummy, dummy, cfg, keys)
     got = disp.cpu().numpy()
     assert corr is None and got.dtype == np.int16
     assert np.array_equal(got, want), f"{(got != want).sum()} of {got.size} disparities differ"
@@ -216,6 +216,31 @@ def test_match_host_and_rows(handle, oracles):
     assert _same(disp.cpu().numpy(), want_d) and _same(corr.cpu().numpy(), want_c)
 
 
+def test_match_host_pipelined(handle, oracles):
+    """bicos_b200_match_host_begin/_end: two frames in flight on two handles, non-contiguous planes too."""
+    import libbicos_b200 as lb
+
+    kw = dict(nxcorr_threshold=0.9, subpixel_step=0.2, min_variance=2.0)
+    frames = [synth.make_stacks(17, 400, 192, np.uint16, seed=8, frame=f)[:2] for f in range(3)]
+    want = [oracles.port.match(l, r, **kw) for l, r in frames]
+    other = lb.Handle(0)
+    hs = [handle, other]
+    got = []
+    for f, (l, r) in enumerate(frames):
+        hs[f % 2].match_host_end()
+        if f == 2:  # planes that are not back to back in memory: the per-plane upload path
+            l = np.ascontiguousarray(np.concatenate([l, l], axis=1))[:, :400]
+            assert not l.flags.c_contiguous
+        got.append(hs[f % 2].match_host_begin(l, r, Config(**kw)))
+    with pytest.raises(lb.BicosError, match="already in flight"):
+        hs[0].match_host_begin(frames[0][0], frames[0][1], Config(**kw))
+    for x in hs:
+        x.match_host_end()
+    for (d, c), (wd, wc) in zip(got, want):
+        assert _same(d, wd) and _same(c, wc)
+    other.close()
+
+
 def test_errors(handle):
     import torch
 
@@ -261,8 +286,8 @@ def test_gpu_matches_golden_reference_outputs(handle, name):
     d0, k = handle.transform(l, cfg.mode_full)
     d1, _ = handle.transform(r, cfg.mode_full)
     assert np.array_equal(_words(d0, k, cols), g["desc0"]) and np.array_equal(_words(d1, k, cols), g["desc1"])
-    fwd, revf, revl = handle.search(d0, d1, k, cols, cfg.flags)
-    disp, corr, raw = handle.refine(l, r, cfg, fwd, revf, revl)
+    keys = handle.search(d0, d1, k, cols, cfg.flags)
+    disp, corr, raw = handle.refine(l, r, cfg, keys)
     assert np.array_equal(raw.cpu().numpy(), g["raw"])
     assert _same(disp.cpu().numpy(), g["disp"])
     if corr is not None:

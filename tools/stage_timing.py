@@ -58,8 +58,8 @@ def main():
         (dict(nxcorr_threshold=0.96, min_variance=2.0, subpixel_step=0.1, double=True), "agree_subpixel 0.1 f64"),
     ):
         cfg = lb.Config(**kw)
-        fwd, revf, revl = h.search(d0, d1, k, args.cols, cfg.flags)
-        med, mn = timeit(lambda: h.refine(l, r, cfg, fwd, revf, revl, want_raw=False), iters=5, warmup=2)
+        keys = h.search(d0, d1, k, args.cols, cfg.flags)
+        med, mn = timeit(lambda: h.refine(l, r, cfg, keys, want_raw=False), iters=5, warmup=2)
         print(f"refine {name:24s}: {med:.3f} ms (min {mn:.3f})")
     for kw, name in (
         (dict(nxcorr_threshold=0.96, min_variance=2.0), "config1 (NoDuplicates, integer)"),
