@@ -224,8 +224,6 @@ size_t desc_pitch_for(int cols, int K) {
     return ((size_t)cols * K + 3) & ~(size_t)3; // rows start 16 B aligned
 }
 
-constexpr size_t KEYS_HEADER = 16; // the search kernel's work counter sits in front of the key arrays
-
 int key_arrays(int flags) {
     return 1 + ((flags & FLAG_NODUPES) ? 1 : 0) + ((flags & FLAG_CONSISTENCY) ? ((flags & FLAG_NODUPES) ? 2 : 1) : 0);
 }
@@ -288,6 +286,7 @@ int do_refine(
     prm.subpixel = prm.has_threshold && cfg->subpixel_step >= 0;
     prm.nsteps = 0;
     prm.xs = nullptr;
+    prm.one = 1.0f;
     if (prm.subpixel) {
         if (int rc = prepare_steps(h, cfg->subpixel_step, stream))
             return rc;
@@ -352,7 +351,7 @@ int do_match(
     // key arrays, contiguous so that one memset initialises them: fwd_first, then fwd_last
     // (NODUPES), rev_first (CONSISTENCY), rev_last (both)
     const int n_keys = key_arrays(flags);
-    CU(h->keys.reserve(KEYS_HEADER + px * sizeof(uint32_t) * n_keys));
+    CU(h->keys.reserve(px * sizeof(uint32_t) * n_keys));
 
     uint32_t* d0 = static_cast<uint32_t*>(h->desc0.ptr);
     uint32_t* d1 = static_cast<uint32_t*>(h->desc1.ptr);
@@ -365,10 +364,9 @@ int do_match(
     if (int rc = prof_mark(h, stream))
         return rc;
 
-    KeyArrays ka = split_keys(reinterpret_cast<uint32_t*>(static_cast<char*>(h->keys.ptr) + KEYS_HEADER), px, flags);
-    CU(cudaMemsetAsync(h->keys.ptr, 0xFF, KEYS_HEADER + px * sizeof(uint32_t) * n_keys, stream)); // work counter + keys
-    CU(launch_search(d0, d1, K, nrows, cols, dpw, flags, static_cast<unsigned long long*>(h->keys.ptr), ka.fwd_first,
-                     ka.fwd_last, ka.rev_first, ka.rev_last, stream));
+    KeyArrays ka = split_keys(static_cast<uint32_t*>(h->keys.ptr), px, flags);
+    CU(cudaMemsetAsync(h->keys.ptr, 0xFF, px * sizeof(uint32_t) * n_keys, stream));
+    CU(launch_search(d0, d1, K, nrows, cols, dpw, flags, ka.fwd_first, ka.fwd_last, ka.rev_first, ka.rev_last, stream));
     h->launches += 1;
     if (int rc = prof_mark(h, stream))
         return rc;
@@ -507,8 +505,6 @@ int bicos_b200_search(bicos_b200_handle h, const uint32_t* desc0, const uint32_t
     DeviceGuard g(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t bytes = (size_t)rows * cols * sizeof(uint32_t);
-    CU(h->keys.reserve(KEYS_HEADER));
-    CU(cudaMemsetAsync(h->keys.ptr, 0xFF, KEYS_HEADER, s)); // work counter
     CU(cudaMemsetAsync(fwd_first, 0xFF, bytes, s));
     if (flags & FLAG_NODUPES)
         CU(cudaMemsetAsync(fwd_last, 0xFF, bytes, s));
@@ -517,8 +513,7 @@ int bicos_b200_search(bicos_b200_handle h, const uint32_t* desc0, const uint32_t
         if (flags & FLAG_NODUPES)
             CU(cudaMemsetAsync(rev_last, 0xFF, bytes, s));
     }
-    CU(launch_search(desc0, desc1, K, rows, cols, desc_pitch_words, flags, static_cast<unsigned long long*>(h->keys.ptr),
-                     fwd_first, fwd_last, rev_first, rev_last, s));
+    CU(launch_search(desc0, desc1, K, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, s));
     h->launches += 1;
     return 0;
 }
@@ -651,7 +646,7 @@ int bicos_b200_match_host_begin(bicos_b200_handle h, const void* const* host_pla
             CU(h->stage_corr.reserve((size_t)rows * cols * corr_eb));
         CU(h->desc0.reserve(dpw * band_rows_max * sizeof(uint32_t)));
         CU(h->desc1.reserve(dpw * band_rows_max * sizeof(uint32_t)));
-        CU(h->keys.reserve(KEYS_HEADER + px * sizeof(uint32_t) * 4));
+        CU(h->keys.reserve(px * sizeof(uint32_t) * 4));
         if (cfg->nxcorr_threshold >= 0 && cfg->subpixel_step >= 0)
             if (int rc = prepare_steps(h, cfg->subpixel_step, h->s_compute))
                 return rc;

@@ -44,6 +44,7 @@ struct RefineParams {
     int subpixel;
     int nsteps; // number of x values of the float loop x=-1; x<=1; x+=step
     const float* xs; // device array [nsteps] with exactly those float values
+    float one; // 1.0f, passed at run time so that ptxas cannot fold x * one (refine.cu, fma2 note)
     int nodupes_forward; // forward search must be unique: compare fwd_first with fwd_last
     const uint32_t* fwd_first;
     const uint32_t* fwd_last;
@@ -74,8 +75,7 @@ cudaError_t launch_transform(
 // kernel 2: row-wise Hamming argmin, forward (per left pixel) and, with
 // FLAG_CONSISTENCY, the column-wise minima of the same W x W cost tile (reference a5/a6/a7).
 // All key arrays in use must be pre-filled with KEY_NONE by the caller (fwd_last / rev_last
-// are only touched with FLAG_NODUPES, rev_* only with FLAG_CONSISTENCY), and *work_counter
-// (the persistent grid's work queue) with all-ones: one memset of 0xFF covers both.
+// are only touched with FLAG_NODUPES, rev_* only with FLAG_CONSISTENCY).
 cudaError_t launch_search(
     const uint32_t* desc0,
     const uint32_t* desc1,
@@ -84,7 +84,6 @@ cudaError_t launch_search(
     int cols,
     size_t desc_pitch_words,
     int flags,
-    unsigned long long* work_counter,
     uint32_t* fwd_first,
     uint32_t* fwd_last,
     uint32_t* rev_first,

@@ -6,14 +6,13 @@
 //
 // Work = rows x units x columns: a unit is a block of 128*A left pixels of one row, whose
 // descriptors a CTA keeps in registers (A per thread) while the right row streams through
-// shared memory in chunks, read with warp-uniform (broadcast) vector loads. The grid is
-// persistent -- (resident CTAs per SM) x (SM count) CTAs -- and the CTAs draw contiguous ranges
-// of (row, unit, column) steps from one atomic counter, each draw 1/(2G) of what is left
-// (guided self-scheduling), so that all SMs finish together whatever the image size: a
-// one-CTA-per-unit grid lost 8 % to the last partial wave at 2048x1536, and a static equal
-// split loses as much because the warp schedulers do not serve co-resident CTAs evenly. A unit
-// whose column range is split between CTAs is merged with atomicMin; A is chosen per image
-// width so that units tile the row with the least padding (1280 and 1920 columns: A = 5).
+// shared memory in chunks, read with warp-uniform (broadcast) vector loads. One CTA handles one
+// unit, or 1/splits of its columns when the image has too few units to give every SM its
+// share of CTAs (row bands of the host pipeline, row shards on 8 GPUs); the pieces of a split
+// unit are merged with atomicMin. A is chosen per image width so that units tile the row with
+// the least padding (1280 and 1920 columns: A = 5). The kernel is bound by the POPC pipe, so
+// an SM that is left with fewer CTAs near the end simply runs them faster: a persistent grid
+// with a work queue (tried, tools/search_tune.cu history) was 5 % slower than this plain grid.
 //
 // Exactness without the reference's serial scan:
 //  * key = cost << 16 | column. min(key) over any partition of the row is the lowest cost
@@ -41,7 +40,8 @@ namespace {
 constexpr int THREADS = 128;
 constexpr int CHUNK_BYTES = 16 * 1024; // right-row descriptor bytes staged per pass
 constexpr int STEP_ALIGN = 8; // CTA shares start on multiples of 8 columns (16 B aligned staging for every K)
-constexpr int MIN_TAKE = 256; // smallest range a CTA draws from the work counter (columns of one unit)
+constexpr int CTAS_PER_SM_WANTED = 20; // split units until the grid has about this many CTAs per SM
+constexpr int MAX_SPLITS = 8;
 
 __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
@@ -109,75 +109,58 @@ __device__ __forceinline__ uint32_t hamming(const Desc<K>& l, const Desc<K>& r) 
     }
 }
 
-template<int K, int FLAGS, int A>
-__global__ void __launch_bounds__(THREADS) search_kernel(
-    const uint32_t* __restrict__ desc0,
-    const uint32_t* __restrict__ desc1,
-    int cols,
-    size_t pitch_words,
-    int chunk, // right descriptors staged per pass
-    int units_per_row,
-    int steps_per_unit, // cols rounded up to STEP_ALIGN
-    long long total_steps, // rows * units_per_row * steps_per_unit
-    unsigned long long* __restrict__ work_counter, // steps handed out so far, minus one (starts at ~0)
-    uint32_t* __restrict__ fwd_first,
-    uint32_t* __restrict__ fwd_last,
-    uint32_t* __restrict__ rev_first,
-    uint32_t* __restrict__ rev_last
-) {
+struct SearchArgs {
+    const uint32_t* desc0;
+    const uint32_t* desc1;
+    int cols;
+    size_t pitch_words;
+    int chunk; // right descriptors staged per pass
+    int units_per_row;
+    int steps_per_unit; // cols rounded up to STEP_ALIGN
+    long long total_steps; // rows * units_per_row * steps_per_unit
+    int splits; // CTAs per unit
+    uint32_t* fwd_first;
+    uint32_t* fwd_last;
+    uint32_t* rev_first;
+    uint32_t* rev_last;
+};
+
+// All steps [s, s_end) of the (row, unit, column) space, unit by unit.
+template<int K, int FLAGS, int A, int NT, int UNROLL>
+__device__ __forceinline__ void search_range(const SearchArgs& p, long long s, const long long s_end, uint4* smem_raw) {
     constexpr bool NODUPES = (FLAGS & FLAG_NODUPES) != 0;
     constexpr bool REVERSE = (FLAGS & FLAG_CONSISTENCY) != 0;
-    constexpr int UNIT = THREADS * A; // left pixels per unit
+    constexpr int UNIT = NT * A; // left pixels per unit
 
-    extern __shared__ uint4 smem_raw[];
     uint32_t* const s_right = reinterpret_cast<uint32_t*>(smem_raw);
-    uint32_t* const s_colf = s_right + (size_t)chunk * K;
-    uint32_t* const s_coll = s_colf + chunk;
+    uint32_t* const s_colf = s_right + (size_t)p.chunk * K;
+    uint32_t* const s_coll = s_colf + p.chunk;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-
-    __shared__ long long s_range[2];
-    const long long G = gridDim.x;
-
-    for (;;) {
-    // ---- draw the next range of steps: half of an equal share of what is left ------------------
-    __syncthreads(); // everyone is done with the previous range (and with s_range)
-    if (tid == 0) {
-        const long long handed_out = (long long)(*reinterpret_cast<volatile unsigned long long*>(work_counter) + 1ULL);
-        long long take = (total_steps - handed_out) / (2 * G);
-        take = (take < MIN_TAKE ? MIN_TAKE : take) & ~(long long)(STEP_ALIGN - 1);
-        const long long first = (long long)(atomicAdd(work_counter, (unsigned long long)take) + 1ULL);
-        s_range[0] = first;
-        s_range[1] = min(total_steps, first + take);
-    }
-    __syncthreads();
-    long long s = s_range[0];
-    const long long s_end = s_range[1];
-    if (s >= total_steps)
-        break;
+    const int cols = p.cols;
 
     while (s < s_end) {
-        const long long ru = s / steps_per_unit;
-        const int jb = (int)(s - ru * steps_per_unit);
-        const int je = (int)min((long long)steps_per_unit, jb + (s_end - s));
+        const long long ru = s / p.steps_per_unit;
+        const int jb = (int)(s - ru * p.steps_per_unit);
+        const int je = (int)min((long long)p.steps_per_unit, jb + (s_end - s));
         s += je - jb;
         const int j_end = min(je, cols);
         if (jb >= j_end)
             continue; // only the alignment padding of this unit was left
-        const int row = (int)(ru / units_per_row);
-        const int unit = (int)(ru - (long long)row * units_per_row);
-        const bool whole = jb == 0 && je == steps_per_unit; // no other CTA works on this unit
+        const int row = (int)(ru / p.units_per_row);
+        const int unit = (int)(ru - (long long)row * p.units_per_row);
+        const bool whole = jb == 0 && je == p.steps_per_unit; // no other CTA works on this unit
 
-        const uint32_t* const row0 = desc0 + (size_t)row * pitch_words;
-        const uint32_t* const row1 = desc1 + (size_t)row * pitch_words;
+        const uint32_t* const row0 = p.desc0 + (size_t)row * p.pitch_words;
+        const uint32_t* const row1 = p.desc1 + (size_t)row * p.pitch_words;
 
         Desc<K> l[A];
         uint32_t icol[A], icol_rev[A];
         uint32_t mf[A], ml[A];
 #pragma unroll
         for (int a = 0; a < A; ++a) {
-            const int i = unit * UNIT + a * THREADS + tid;
+            const int i = unit * UNIT + a * NT + tid;
             const bool valid = i < cols;
             l[a] = load_desc<K>(row0 + (size_t)(valid ? i : cols - 1) * K);
             // lanes past the end of the row carry bit 31 so that they never win a column minimum
@@ -187,18 +170,18 @@ __global__ void __launch_bounds__(THREADS) search_kernel(
             ml[a] = KEY_NONE;
         }
 
-        for (int j0 = jb; j0 < j_end; j0 += chunk) {
-            const int cnt = min(chunk, j_end - j0);
+        for (int j0 = jb; j0 < j_end; j0 += p.chunk) {
+            const int cnt = min(p.chunk, j_end - j0);
             __syncthreads(); // previous chunk fully consumed and flushed
 
             // stage the right descriptors [j0, j0+cnt) (rows are 16 B aligned and padded)
             {
                 const uint4* src = reinterpret_cast<const uint4*>(row1 + (size_t)j0 * K);
                 const int nvec = (cnt * K + 3) / 4;
-                for (int v = tid; v < nvec; v += THREADS)
+                for (int v = tid; v < nvec; v += NT)
                     smem_raw[v] = src[v];
                 if constexpr (REVERSE) {
-                    for (int v = tid; v < cnt; v += THREADS) {
+                    for (int v = tid; v < cnt; v += NT) {
                         s_colf[v] = KEY_NONE;
                         if constexpr (NODUPES)
                             s_coll[v] = KEY_NONE;
@@ -207,41 +190,56 @@ __global__ void __launch_bounds__(THREADS) search_kernel(
             }
             __syncthreads();
 
-#pragma unroll 2
-            for (int jj = 0; jj < cnt; ++jj) {
-                const Desc<K> r = load_desc<K>(s_right + (size_t)jj * K); // warp-uniform: broadcast
-                const uint32_t j = (uint32_t)(j0 + jj);
-                const uint32_t jrev = 65535u - j;
-                uint32_t ck = KEY_NONE, ckl = KEY_NONE;
+            // Columns in groups of 32: lane u of every warp keeps the warp's minimum over its
+            // 32*A left pixels for column u of the group, and one conflict-free shared-memory
+            // atomic per group merges the warps (a per-column atomic from one lane would share
+            // the MIO queue with the POPCs that bound this kernel).
+            for (int jj0 = 0; jj0 < cnt; jj0 += 32) {
+                const int m = min(32, cnt - jj0);
+                uint32_t colf = KEY_NONE, coll = KEY_NONE;
+#pragma unroll(UNROLL)
+                for (int u = 0; u < m; ++u) {
+                    const Desc<K> r = load_desc<K>(s_right + (size_t)(jj0 + u) * K); // warp-uniform: broadcast
+                    const uint32_t j = (uint32_t)(j0 + jj0 + u);
+                    const uint32_t jrev = 65535u - j;
+                    uint32_t ck = KEY_NONE, ckl = KEY_NONE;
 #pragma unroll
-                for (int a = 0; a < A; ++a) {
-                    const uint32_t cost16 = hamming<K>(l[a], r) << 16;
-                    mf[a] = min(mf[a], cost16 + j);
-                    if constexpr (NODUPES)
-                        ml[a] = min(ml[a], cost16 + jrev);
-                    if constexpr (REVERSE) {
-                        ck = min(ck, cost16 + icol[a]);
+                    for (int a = 0; a < A; ++a) {
+                        const uint32_t cost16 = hamming<K>(l[a], r) << 16;
+                        mf[a] = min(mf[a], cost16 + j);
                         if constexpr (NODUPES)
-                            ckl = min(ckl, cost16 + icol_rev[a]);
+                            ml[a] = min(ml[a], cost16 + jrev);
+                        if constexpr (REVERSE) {
+                            ck = min(ck, cost16 + icol[a]);
+                            if constexpr (NODUPES)
+                                ckl = min(ckl, cost16 + icol_rev[a]);
+                        }
+                    }
+                    if constexpr (REVERSE) {
+                        ck = __reduce_min_sync(0xFFFFFFFFu, ck);
+                        if (lane == u)
+                            colf = ck;
+                        if constexpr (NODUPES) {
+                            ckl = __reduce_min_sync(0xFFFFFFFFu, ckl);
+                            if (lane == u)
+                                coll = ckl;
+                        }
                     }
                 }
                 if constexpr (REVERSE) {
-                    ck = __reduce_min_sync(0xFFFFFFFFu, ck);
-                    if constexpr (NODUPES)
-                        ckl = __reduce_min_sync(0xFFFFFFFFu, ckl);
-                    if (lane == 0) {
-                        atomicMin(&s_colf[jj], ck);
+                    if (lane < m) {
+                        atomicMin(&s_colf[jj0 + lane], colf);
                         if constexpr (NODUPES)
-                            atomicMin(&s_coll[jj], ckl);
+                            atomicMin(&s_coll[jj0 + lane], coll);
                     }
                 }
             }
 
             if constexpr (REVERSE) {
                 __syncthreads();
-                uint32_t* const gf = rev_first + (size_t)row * cols + j0;
-                uint32_t* const gl = rev_last + (size_t)row * cols + j0;
-                for (int v = tid; v < cnt; v += THREADS) {
+                uint32_t* const gf = p.rev_first + (size_t)row * cols + j0;
+                uint32_t* const gl = p.rev_last + (size_t)row * cols + j0;
+                for (int v = tid; v < cnt; v += NT) {
                     atomicMin(gf + v, s_colf[v]);
                     if constexpr (NODUPES)
                         atomicMin(gl + v, s_coll[v]);
@@ -252,22 +250,35 @@ __global__ void __launch_bounds__(THREADS) search_kernel(
         // forward keys of this unit; the postfilter decodes them (and compares first / last)
 #pragma unroll
         for (int a = 0; a < A; ++a) {
-            const int i = unit * UNIT + a * THREADS + tid;
+            const int i = unit * UNIT + a * NT + tid;
             if (i < cols) {
                 const size_t at = (size_t)row * cols + i;
                 if (whole) {
-                    fwd_first[at] = mf[a];
+                    p.fwd_first[at] = mf[a];
                     if constexpr (NODUPES)
-                        fwd_last[at] = ml[a];
+                        p.fwd_last[at] = ml[a];
                 } else {
-                    atomicMin(fwd_first + at, mf[a]);
+                    atomicMin(p.fwd_first + at, mf[a]);
                     if constexpr (NODUPES)
-                        atomicMin(fwd_last + at, ml[a]);
+                        atomicMin(p.fwd_last + at, ml[a]);
                 }
             }
         }
     }
-    } // next draw
+}
+
+// `splits` CTAs per unit, each an equal slice of the unit's columns.
+template<int K, int FLAGS, int A, int NT, int UNROLL>
+__global__ void __launch_bounds__(NT) search_kernel(const SearchArgs p) {
+    extern __shared__ uint4 smem_raw[];
+    const long long ru = blockIdx.x / p.splits;
+    const int part = blockIdx.x - (int)ru * p.splits;
+    const int span = ((p.steps_per_unit + p.splits - 1) / p.splits + STEP_ALIGN - 1) & ~(STEP_ALIGN - 1);
+    const long long base = ru * p.steps_per_unit;
+    const long long s = base + (long long)part * span;
+    const long long s_end = min(base + p.steps_per_unit, s + span);
+    if (s < s_end)
+        search_range<K, FLAGS, A, NT, UNROLL>(p, s, s_end, smem_raw);
 }
 
 int chunk_for(int K, int cols) {
@@ -304,57 +315,55 @@ int sm_count() {
     return cached_sms;
 }
 
-template<int K, int FLAGS, int A>
+// splits <= 0: chosen here from the grid size
+template<int K, int FLAGS, int A, int NT = THREADS, int UNROLL = 2>
 cudaError_t launch_one(
     const uint32_t* desc0,
     const uint32_t* desc1,
     int rows,
     int cols,
     size_t pitch_words,
-    unsigned long long* work_counter,
     uint32_t* fwd_first,
     uint32_t* fwd_last,
     uint32_t* rev_first,
     uint32_t* rev_last,
-    cudaStream_t stream
+    cudaStream_t stream,
+    int splits = 0
 ) {
-    const int chunk = chunk_for(K, cols);
+    SearchArgs p;
+    p.desc0 = desc0;
+    p.desc1 = desc1;
+    p.cols = cols;
+    p.pitch_words = pitch_words;
+    p.chunk = chunk_for(K, cols);
+    const int unit = NT * A;
+    p.units_per_row = (cols + unit - 1) / unit;
+    p.steps_per_unit = (cols + STEP_ALIGN - 1) / STEP_ALIGN * STEP_ALIGN;
+    p.total_steps = (long long)rows * p.units_per_row * p.steps_per_unit;
+    const long long units = (long long)rows * p.units_per_row;
+    if (splits <= 0) {
+        // about 512 columns per CTA (measured best at 2048 columns: tools/search_tune), down to
+        // 256 when the image has too few units to give every SM its share of CTAs
+        splits = p.steps_per_unit / 512;
+        const long long wanted = (long long)sm_count() * CTAS_PER_SM_WANTED;
+        if (units * splits < wanted)
+            splits = p.steps_per_unit / 256;
+        splits = splits > MAX_SPLITS ? MAX_SPLITS : splits < 1 ? 1 : splits;
+    }
+    p.splits = splits;
+    p.fwd_first = fwd_first;
+    p.fwd_last = fwd_last;
+    p.rev_first = rev_first;
+    p.rev_last = rev_last;
     const int smem = search_smem_bytes(K, cols, FLAGS);
-    auto kernel = search_kernel<K, FLAGS, A>;
+    auto kernel = search_kernel<K, FLAGS, A, NT, UNROLL>;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess)
         return err;
-    int occ = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, THREADS, smem);
-    if (err != cudaSuccess)
-        return err;
-    if (occ < 1)
+    const long long grid = units * p.splits;
+    if (grid <= 0 || grid > 0x7FFFFFFFLL)
         return cudaErrorInvalidConfiguration;
-    const int unit = THREADS * A;
-    const int units_per_row = (cols + unit - 1) / unit;
-    const int steps_per_unit = (cols + STEP_ALIGN - 1) / STEP_ALIGN * STEP_ALIGN;
-    const long long total = (long long)rows * units_per_row * steps_per_unit;
-    long long grid = (long long)sm_count() * occ;
-    const long long most = (total + 2 * MIN_TAKE - 1) / (2 * MIN_TAKE); // tiny images: fewer CTAs
-    if (grid > most)
-        grid = most;
-    if (grid < 1)
-        grid = 1;
-    kernel<<<(unsigned)grid, THREADS, smem, stream>>>(
-        desc0,
-        desc1,
-        cols,
-        pitch_words,
-        chunk,
-        units_per_row,
-        steps_per_unit,
-        total,
-        work_counter,
-        fwd_first,
-        fwd_last,
-        rev_first,
-        rev_last
-    );
+    kernel<<<(unsigned)grid, NT, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -365,7 +374,6 @@ cudaError_t launch_a(
     int rows,
     int cols,
     size_t pitch_words,
-    unsigned long long* work_counter,
     uint32_t* fwd_first,
     uint32_t* fwd_last,
     uint32_t* rev_first,
@@ -374,11 +382,11 @@ cudaError_t launch_a(
 ) {
     switch (pick_a(cols)) {
         case 3:
-            return launch_one<K, FLAGS, 3>(desc0, desc1, rows, cols, pitch_words, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
+            return launch_one<K, FLAGS, 3>(desc0, desc1, rows, cols, pitch_words, fwd_first, fwd_last, rev_first, rev_last, stream);
         case 5:
-            return launch_one<K, FLAGS, 5>(desc0, desc1, rows, cols, pitch_words, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
+            return launch_one<K, FLAGS, 5>(desc0, desc1, rows, cols, pitch_words, fwd_first, fwd_last, rev_first, rev_last, stream);
         default:
-            return launch_one<K, FLAGS, 4>(desc0, desc1, rows, cols, pitch_words, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
+            return launch_one<K, FLAGS, 4>(desc0, desc1, rows, cols, pitch_words, fwd_first, fwd_last, rev_first, rev_last, stream);
     }
 }
 
@@ -390,7 +398,6 @@ cudaError_t launch_k(
     int cols,
     size_t pitch_words,
     int flags,
-    unsigned long long* work_counter,
     uint32_t* fwd_first,
     uint32_t* fwd_last,
     uint32_t* rev_first,
@@ -399,13 +406,13 @@ cudaError_t launch_k(
 ) {
     switch (flags) {
         case FLAG_NODUPES:
-            return launch_a<K, FLAG_NODUPES>(desc0, desc1, rows, cols, pitch_words, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
+            return launch_a<K, FLAG_NODUPES>(desc0, desc1, rows, cols, pitch_words, fwd_first, fwd_last, rev_first, rev_last, stream);
         case FLAG_CONSISTENCY:
-            return launch_a<K, FLAG_CONSISTENCY>(desc0, desc1, rows, cols, pitch_words, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
+            return launch_a<K, FLAG_CONSISTENCY>(desc0, desc1, rows, cols, pitch_words, fwd_first, fwd_last, rev_first, rev_last, stream);
         case FLAG_NODUPES | FLAG_CONSISTENCY:
-            return launch_a<K, FLAG_NODUPES | FLAG_CONSISTENCY>(desc0, desc1, rows, cols, pitch_words, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
+            return launch_a<K, FLAG_NODUPES | FLAG_CONSISTENCY>(desc0, desc1, rows, cols, pitch_words, fwd_first, fwd_last, rev_first, rev_last, stream);
         case 0: // plain first-minimum search (building block, not reachable from Config)
-            return launch_a<K, 0>(desc0, desc1, rows, cols, pitch_words, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
+            return launch_a<K, 0>(desc0, desc1, rows, cols, pitch_words, fwd_first, fwd_last, rev_first, rev_last, stream);
     }
     return cudaErrorInvalidValue;
 }
@@ -428,7 +435,6 @@ cudaError_t launch_search(
     int cols,
     size_t desc_pitch_words,
     int flags,
-    unsigned long long* work_counter,
     uint32_t* fwd_first,
     uint32_t* fwd_last,
     uint32_t* rev_first,
@@ -439,13 +445,13 @@ cudaError_t launch_search(
         return cudaErrorInvalidValue;
     switch (K) {
         case 1:
-            return launch_k<1>(desc0, desc1, rows, cols, desc_pitch_words, flags, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
+            return launch_k<1>(desc0, desc1, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, stream);
         case 2:
-            return launch_k<2>(desc0, desc1, rows, cols, desc_pitch_words, flags, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
+            return launch_k<2>(desc0, desc1, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, stream);
         case 4:
-            return launch_k<4>(desc0, desc1, rows, cols, desc_pitch_words, flags, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
+            return launch_k<4>(desc0, desc1, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, stream);
         case 8:
-            return launch_k<8>(desc0, desc1, rows, cols, desc_pitch_words, flags, work_counter, fwd_first, fwd_last, rev_first, rev_last, stream);
+            return launch_k<8>(desc0, desc1, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, stream);
     }
     return cudaErrorInvalidValue;
 }
