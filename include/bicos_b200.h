@@ -152,6 +152,22 @@ int bicos_b200_match_rows(bicos_b200_handle h, const void* const* planes0,
                           void* disparity, size_t disparity_pitch_bytes, void* corrmap,
                           size_t corrmap_pitch_bytes, void* stream);
 
+/* ---- peer-memory output assembly for a row-sharded match, one process per GPU -------------
+ * Rows are independent, so the only exchange of a row-sharded match is the assembly of the
+ * output rows on one GPU. Instead of a gather after the kernels, the assembling rank allocates
+ * the output images with bicos_b200_shared_alloc and publishes the 64-byte handles (over any
+ * channel: torch.distributed, MPI, a pipe); every other rank maps them once with
+ * bicos_b200_shared_open and passes mapped + row_begin * pitch as the disparity / corrmap
+ * pointer of bicos_b200_match on ITS rows. Its refine kernel then stores its rows straight
+ * into the assembling GPU's memory over NVLink; after a stream synchronisation and a barrier
+ * the result is complete. Inside one process, BICOS::match_sharded does the same with
+ * cudaDeviceEnablePeerAccess. */
+#define BICOS_B200_IPC_HANDLE_BYTES 64
+int bicos_b200_shared_alloc(int device, size_t bytes, void** dev_ptr, void* handle_out);
+int bicos_b200_shared_open(int device, const void* handle, void** dev_ptr);
+int bicos_b200_shared_close(int device, void* dev_ptr); /* for pointers from _shared_open */
+int bicos_b200_shared_free(int device, void* dev_ptr); /* for pointers from _shared_alloc */
+
 /* Blocks until all work enqueued through this handle's internal streams and `stream` is done. */
 int bicos_b200_synchronize(bicos_b200_handle h, void* stream);
 

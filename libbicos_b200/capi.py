@@ -25,7 +25,9 @@ EXPORTS = (
     "bicos_b200_transform", "bicos_b200_search", "bicos_b200_refine", "bicos_b200_match",
     "bicos_b200_match_host", "bicos_b200_match_host_begin", "bicos_b200_match_host_end", "bicos_b200_match_rows", "bicos_b200_synchronize",
     "bicos_b200_kernel_launches", "bicos_b200_set_profiling", "bicos_b200_stage_times",
+    "bicos_b200_shared_alloc", "bicos_b200_shared_open", "bicos_b200_shared_close", "bicos_b200_shared_free",
 )
+IPC_HANDLE_BYTES = 64
 
 
 class BicosError(RuntimeError):
@@ -106,6 +108,10 @@ def lib():
         L.bicos_b200_match_host.argtypes = [vp, pp, pp, i, i, i, i, cfgp, vp, vp]
         L.bicos_b200_match_host_begin.argtypes = [vp, pp, pp, i, i, i, i, cfgp, vp, vp]
         L.bicos_b200_match_host_end.argtypes = [vp]
+        L.bicos_b200_shared_alloc.argtypes = [i, sz, ctypes.POINTER(ctypes.c_void_p), vp]
+        L.bicos_b200_shared_open.argtypes = [i, vp, ctypes.POINTER(ctypes.c_void_p)]
+        L.bicos_b200_shared_close.argtypes = [i, vp]
+        L.bicos_b200_shared_free.argtypes = [i, vp]
         L.bicos_b200_synchronize.argtypes = [vp, vp]
         L.bicos_b200_set_profiling.argtypes = [vp, i]
         L.bicos_b200_stage_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
@@ -271,6 +277,18 @@ class Handle:
                                                int(rows_range[0]), int(rows_range[1]), *args))
         return disp, corr
 
+    def match_raw(self, stack0, stack1, cfg: Config, disp_ptr: int, disp_pitch: int, corr_ptr: Optional[int],
+                  corr_pitch: int) -> None:
+        """Device-resident match writing to raw device addresses (e.g. rows of a peer-mapped image
+        from shared_open): disparity rows at disp_ptr + r * disp_pitch, corrmap likewise."""
+        p0, n, rows, cols, pitch, depth = self._stack_info(stack0)
+        p1, n1, rows1, cols1, pitch1, depth1 = self._stack_info(stack1)
+        if (n1, rows1, cols1, pitch1, depth1) != (n, rows, cols, pitch, depth):
+            raise BicosError("stack0 and stack1 differ in length, size, type or pitch")
+        ccfg = cfg.to_c()
+        _check(lib().bicos_b200_match(self._h, p0, p1, n, rows, cols, pitch, depth, ctypes.byref(ccfg), disp_ptr,
+                                      disp_pitch, corr_ptr, corr_pitch, self._stream()))
+
     def match_host(self, stack0, stack1, cfg: Config, out=None):
         """Host-resident match on numpy arrays / CPU tensors [n, rows, cols]; H2D and D2H included."""
         res = self.match_host_begin(stack0, stack1, cfg, out)
@@ -335,3 +353,56 @@ class Handle:
 
     def synchronize(self) -> None:
         _check(lib().bicos_b200_synchronize(self._h, self._stream()))
+
+
+class SharedImage:
+    """A device image that other processes' GPUs can store into over NVLink (C ABI
+    bicos_b200_shared_*): `SharedImage.create` on the assembling rank, `SharedImage.open(handle)`
+    on the others. `tensor()` aliases the memory as a torch tensor (owner side)."""
+
+    def __init__(self, device: int, ptr: int, rows: int, cols: int, dtype, owner: bool, handle: bytes = b""):
+        self.device, self.ptr, self.rows, self.cols, self.dtype, self.owner, self.handle = \
+            device, ptr, rows, cols, dtype, owner, handle
+
+    @staticmethod
+    def _itemsize(dtype) -> int:
+        import torch
+
+        return torch.empty((), dtype=dtype).element_size()
+
+    @classmethod
+    def create(cls, device: int, rows: int, cols: int, dtype) -> "SharedImage":
+        ptr = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(IPC_HANDLE_BYTES)
+        _check(lib().bicos_b200_shared_alloc(device, rows * cols * cls._itemsize(dtype), ctypes.byref(ptr), handle))
+        return cls(device, ptr.value, rows, cols, dtype, True, handle.raw)
+
+    @classmethod
+    def open(cls, device: int, handle: bytes, rows: int, cols: int, dtype) -> "SharedImage":
+        ptr = ctypes.c_void_p()
+        _check(lib().bicos_b200_shared_open(device, ctypes.create_string_buffer(handle, IPC_HANDLE_BYTES), ctypes.byref(ptr)))
+        return cls(device, ptr.value, rows, cols, dtype, False)
+
+    @property
+    def pitch(self) -> int:
+        return self.cols * self._itemsize(self.dtype)
+
+    def row_ptr(self, row: int) -> int:
+        return self.ptr + row * self.pitch
+
+    def tensor(self):
+        import torch
+
+        typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int16: "<i2"}[self.dtype]
+
+        class _Alias:
+            __cuda_array_interface__ = {"shape": (self.rows, self.cols), "typestr": typestr,
+                                        "data": (self.ptr, False), "version": 2}
+
+        return torch.as_tensor(_Alias(), device=torch.device("cuda", self.device))
+
+    def close(self) -> None:
+        if self.ptr:
+            fn = lib().bicos_b200_shared_free if self.owner else lib().bicos_b200_shared_close
+            _check(fn(self.device, self.ptr))
+            self.ptr = 0

@@ -718,6 +718,58 @@ int bicos_b200_match_host(bicos_b200_handle h, const void* const* host_planes0,
     return bicos_b200_match_host_end(h);
 }
 
+// ---- peer-memory output assembly (one process per GPU) ------------------------------------------
+
+int bicos_b200_shared_alloc(int device, size_t bytes, void** dev_ptr, void* handle_out) {
+    if (!dev_ptr || !handle_out || bytes == 0)
+        return fail(BICOS_B200_ERR_INVALID, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == BICOS_B200_IPC_HANDLE_BYTES, "IPC handle size");
+    DeviceGuard g(device);
+    if (!g.ok)
+        return fail(BICOS_B200_ERR_CUDA, "cannot select device %d", device);
+    void* p = nullptr;
+    CU(cudaMalloc(&p, bytes)); // a dedicated allocation: IPC handles name whole allocations
+    cudaIpcMemHandle_t hd;
+    const cudaError_t err = cudaIpcGetMemHandle(&hd, p);
+    if (err != cudaSuccess) {
+        cudaFree(p);
+        return cuda_fail(err, "cudaIpcGetMemHandle");
+    }
+    std::memcpy(handle_out, &hd, sizeof hd);
+    *dev_ptr = p;
+    return 0;
+}
+
+int bicos_b200_shared_open(int device, const void* handle, void** dev_ptr) {
+    if (!handle || !dev_ptr)
+        return fail(BICOS_B200_ERR_INVALID, "null argument");
+    DeviceGuard g(device);
+    if (!g.ok)
+        return fail(BICOS_B200_ERR_CUDA, "cannot select device %d", device);
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handle, sizeof hd);
+    CU(cudaIpcOpenMemHandle(dev_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int bicos_b200_shared_close(int device, void* dev_ptr) {
+    if (!dev_ptr)
+        return 0;
+    DeviceGuard g(device);
+    CU(cudaDeviceSynchronize());
+    CU(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+
+int bicos_b200_shared_free(int device, void* dev_ptr) {
+    if (!dev_ptr)
+        return 0;
+    DeviceGuard g(device);
+    CU(cudaDeviceSynchronize());
+    CU(cudaFree(dev_ptr));
+    return 0;
+}
+
 int bicos_b200_set_profiling(bicos_b200_handle h, int enabled) {
     if (!h)
         return fail(BICOS_B200_ERR_INVALID, "null handle");

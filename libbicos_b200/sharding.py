@@ -8,7 +8,8 @@ bicos.hpp:91-94, agree.hpp:83,154-156), so
   * a batch of stereo stacks is frame-sharded with no data-path communication at all.
 
 torch.distributed is plumbing (NCCL on GPUs, gloo in the CPU tests); the matching itself is the
-`match_fn` passed in, by default Handle.match from libbicos_b200.capi.
+`match_fn` passed in, by default Handle.match from libbicos_b200.capi. On GPUs the gather can be
+replaced by PeerAssembly: the kernels store their rows straight into rank 0's images over NVLink.
 """
 
 from __future__ import annotations
@@ -71,6 +72,74 @@ def match_row_sharded(match_fn: Callable, stack0_rows, stack1_rows, rows: int, d
     full_disp = gather_rows(disp, rows, dst, group)
     full_corr = gather_rows(corr, rows, dst, group) if corr is not None else None
     return full_disp, full_corr
+
+
+class PeerAssembly:
+    """Output assembly over NVLink peer memory for row-sharded matches (one process per GPU).
+
+    Rank `dst` owns the full-size disparity / corrmap images; every other rank maps them once
+    (CUDA IPC, C ABI bicos_b200_shared_*) and its refine kernel stores its rows straight into
+    them, so a match needs no gather afterwards: only a stream synchronisation and a barrier.
+    Build it once per image size / output types and reuse it for every match.
+    """
+
+    def __init__(self, handle, rows: int, cols: int, cfg, device: int, dst: int = 0, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from .capi import TYPE_16S, TYPE_64F, SharedImage, lib
+        import ctypes
+
+        self.handle, self.rows, self.cols, self.cfg, self.dst, self.group = handle, rows, cols, cfg, dst, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        ccfg = cfg.to_c()
+        dt = lib().bicos_b200_disparity_type(ctypes.byref(ccfg))
+        ct = lib().bicos_b200_corrmap_type(ctypes.byref(ccfg))
+        disp_dtype = torch.int16 if dt == TYPE_16S else torch.float32
+        corr_dtype = None if not ct else (torch.float64 if ct == TYPE_64F else torch.float32)
+        handles = [None, None]
+        if self.rank == dst:
+            self.disp = SharedImage.create(device, rows, cols, disp_dtype)
+            self.corr = SharedImage.create(device, rows, cols, corr_dtype) if corr_dtype is not None else None
+            handles = [self.disp.handle, self.corr.handle if self.corr else None]
+        dist.broadcast_object_list(handles, src=dst, group=group)
+        if self.rank != dst:
+            self.disp = SharedImage.open(device, handles[0], rows, cols, disp_dtype)
+            self.corr = SharedImage.open(device, handles[1], rows, cols, corr_dtype) if handles[1] else None
+        self.lo, self.hi = row_range(self.rank, self.world, rows)
+
+    def match(self, stack0_rows, stack1_rows):
+        """Enqueue this rank's rows ([n, my_rows, W]) of one match; results land on rank `dst`."""
+        if stack0_rows.shape[1] != self.hi - self.lo:
+            raise ValueError(f"rank {self.rank} holds {stack0_rows.shape[1]} rows, expected {self.hi - self.lo}")
+        self.handle.match_raw(stack0_rows, stack1_rows, self.cfg, self.disp.row_ptr(self.lo), self.disp.pitch,
+                              self.corr.row_ptr(self.lo) if self.corr else None, self.corr.pitch if self.corr else 0)
+
+    def finish(self):
+        """Wait for every rank's rows. Returns (disparity, corrmap) tensors aliasing the assembled
+        images on rank `dst`, (None, None) elsewhere."""
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        if self.rank != self.dst:
+            return None, None
+        return self.disp.tensor(), (self.corr.tensor() if self.corr else None)
+
+    def close(self):
+        import torch.distributed as dist
+
+        dist.barrier(group=self.group)  # nobody may still be storing into the owner's memory
+        if self.rank != self.dst:
+            self.disp.close()
+            if self.corr:
+                self.corr.close()
+        dist.barrier(group=self.group)  # mappings are gone before the owner frees
+        if self.rank == self.dst:
+            self.disp.close()
+            if self.corr:
+                self.corr.close()
 
 
 def match_frames_sharded(match_fn: Callable, load_frame: Callable[[int], Sequence], frames: int,

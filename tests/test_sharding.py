@@ -77,3 +77,52 @@ def test_row_and_frame_sharding_world2(tmp_path, oracles):
     for f in frames:
         a, b, _ = synth.make_stacks(N, 12, COLS, np.uint8, seed=21, frame=f)
         assert np.array_equal(np.load(tmp_path / f"frame_{f}.npy"), oracles.port.match(a, b, **KW)[0], equal_nan=True)
+
+
+# ------------------------------------------------------------------ GPUs: NCCL + peer memory --
+def _gpu_worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    import libbicos_b200 as lb
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        cfg = lb.Config(**KW)
+        h = lb.Handle(rank)
+        rows, cols, n = 203, 320, 33  # uneven blocks
+        lo, hi = sharding.row_range(rank, world, rows)
+        l, r, _ = synth.make_stacks(n, rows, cols, np.uint8, seed=33, row0=lo, rows=hi - lo, xp=torch, device="cuda")
+        # (1) kernels store their rows into rank 0's images over NVLink peer memory
+        pa = sharding.PeerAssembly(h, rows, cols, cfg, rank)
+        for _ in range(2):  # reuse of the mapping
+            pa.match(l, r)
+            pd, pc = pa.finish()
+        # (2) the same through a NCCL gather
+        gd, gc = sharding.match_row_sharded(lambda a, b: h.match(a, b, cfg), l, r, rows)
+        if rank == 0:
+            np.save(os.path.join(tmp, "peer_disp.npy"), pd.cpu().numpy())
+            np.save(os.path.join(tmp, "peer_corr.npy"), pc.cpu().numpy())
+            np.save(os.path.join(tmp, "gather_disp.npy"), gd.cpu().numpy())
+            np.save(os.path.join(tmp, "gather_corr.npy"), gc.cpu().numpy())
+        else:
+            assert pd is None and gd is None
+        pa.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_row_sharded_match_on_two_gpus(tmp_path, oracles):
+    """World size 2 over NCCL on real GPUs: peer-memory assembly and gather both equal the oracle."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    world = 2
+    port = 29600 + os.getpid() % 2000
+    mp.spawn(_gpu_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    l, r, _ = synth.make_stacks(33, 203, 320, np.uint8, seed=33)
+    want_d, want_c = oracles.port.match(l, r, **KW)
+    for kind in ("peer", "gather"):
+        assert np.array_equal(np.load(tmp_path / f"{kind}_disp.npy"), want_d, equal_nan=True), kind
+        assert np.array_equal(np.load(tmp_path / f"{kind}_corr.npy"), want_c, equal_nan=True), kind
