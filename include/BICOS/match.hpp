@@ -15,8 +15,9 @@
 // Errors: BICOS::Exception for n < 2, bad depths and CUDA failures; std::invalid_argument
 // when the stack needs more than 256 descriptor bits -- as in the reference
 // (src/impl/cpu.cpp:110-114,154-155; include/impl/cuda/cutil.cuh:32-41). Deviations:
-// mismatching image sizes/types inside a stack throw (undefined behaviour in the reference),
-// and a negative nxcorr_threshold means "unset" as it does in the reference's own C ABI.
+// mismatching image sizes/types inside a stack throw (undefined behaviour in the reference).
+// A negative nxcorr_threshold is honoured as a threshold here (the NXC is evaluated, nothing is
+// rejected); only the Python C ABI keeps the reference's "negative = unset" (src/pybicos_c.cpp:59-69).
 #pragma once
 
 #include "common.hpp"

@@ -48,7 +48,8 @@ typedef enum {
 #define BICOS_B200_FLAG_CONSISTENCY 2
 
 /* Same fields, order and "negative float = unset" convention as the reference's BicosConfig
- * (src/pybicos_c.cpp:30-41 with BICOS_CUDA defined; pybicos/__init__.py:41-51). */
+ * (src/pybicos_c.cpp:30-41 with BICOS_CUDA defined; pybicos/__init__.py:41-51), plus one
+ * trailing extension field. Zero-initialise the struct. */
 typedef struct {
     float nxcorr_threshold; /* < 0: no NXC stage, int16 result (Config::nxcorr_threshold = nullopt) */
     float subpixel_step; /* < 0: integer disparities */
@@ -58,6 +59,10 @@ typedef struct {
     int variant_type; /* 0 = Variant::NoDuplicates, 1 = Variant::Consistency */
     int max_lr_diff; /* Consistency only */
     int no_dupes; /* Consistency only */
+    /* extension, after the reference's fields: nonzero = nxcorr_threshold is a real threshold even
+     * though it is negative (BICOS::Config{.nxcorr_threshold = -1.0f}: "evaluate the NXC, reject
+     * nothing", what the reference CLI uses for --corrmap without --threshold, cli.cpp:150-153) */
+    int negative_threshold_is_set;
 } bicos_b200_config;
 
 typedef struct bicos_b200_handle_s* bicos_b200_handle;

@@ -46,6 +46,7 @@ class CConfig(ctypes.Structure):
         ("variant_type", ctypes.c_int),
         ("max_lr_diff", ctypes.c_int),
         ("no_dupes", ctypes.c_int),
+        ("negative_threshold_is_set", ctypes.c_int),  # extension, see include/bicos_b200.h
     ]
 
 
@@ -66,9 +67,10 @@ class Config:
         def opt(v):
             return -1.0 if v is None else float(v)
 
+        negative = self.nxcorr_threshold is not None and not self.nxcorr_threshold >= 0
         return CConfig(opt(self.nxcorr_threshold), opt(self.subpixel_step), opt(self.min_variance),
                        int(self.mode_full), int(self.double), int(self.consistency),
-                       int(self.max_lr_diff), int(self.no_dupes))
+                       int(self.max_lr_diff), int(self.no_dupes), int(negative))
 
     @property
     def flags(self) -> int:

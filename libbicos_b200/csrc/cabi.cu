@@ -105,6 +105,11 @@ int words_for_bits(int bits) {
     return -1;
 }
 
+// is the NXC stage on? (see bicos_b200_config::negative_threshold_is_set)
+bool has_thr(const bicos_b200_config* cfg) {
+    return cfg->nxcorr_threshold >= 0 || cfg->negative_threshold_is_set != 0;
+}
+
 size_t depth_bytes(int depth) {
     return depth == BICOS_B200_16U ? 2 : 1;
 }
@@ -150,7 +155,7 @@ int validate_common(int n, int rows, int cols, int depth, const bicos_b200_confi
         return fail(BICOS_B200_ERR_INVALID, "empty images");
     if (cols > 32767 || rows > 65535)
         return fail(BICOS_B200_ERR_INVALID, "image too large: at most 32767 columns (int16 disparity) and 65535 rows");
-    if (cfg->nxcorr_threshold >= 0 && cfg->subpixel_step == 0.0f)
+    if (has_thr(cfg) && cfg->subpixel_step == 0.0f)
         return fail(BICOS_B200_ERR_INVALID, "subpixel_step must be positive (the reference loops forever on 0)");
     if (K_out)
         *K_out = K;
@@ -279,7 +284,7 @@ int do_refine(
     prm.consistency = cfg->variant_type != 0;
     prm.nodupes_reverse = prm.consistency && cfg->no_dupes;
     prm.max_lr_diff = cfg->max_lr_diff;
-    prm.has_threshold = cfg->nxcorr_threshold >= 0;
+    prm.has_threshold = has_thr(cfg);
     prm.threshold = cfg->nxcorr_threshold;
     prm.has_minvar = cfg->min_variance >= 0;
     prm.minvar_times_n = prm.has_minvar ? cfg->min_variance * (float)n : 0.f; // cpu.cpp:127
@@ -454,11 +459,11 @@ int bicos_b200_descriptor_words(int n, int mode) {
 }
 
 int bicos_b200_disparity_type(const bicos_b200_config* cfg) {
-    return cfg->nxcorr_threshold >= 0 ? BICOS_B200_32F : BICOS_B200_16S;
+    return has_thr(cfg) ? BICOS_B200_32F : BICOS_B200_16S;
 }
 
 int bicos_b200_corrmap_type(const bicos_b200_config* cfg) {
-    if (cfg->nxcorr_threshold < 0)
+    if (!has_thr(cfg))
         return 0;
     return cfg->precision != 0 ? BICOS_B200_64F : BICOS_B200_32F;
 }
@@ -630,9 +635,9 @@ int bicos_b200_match_host_begin(bicos_b200_handle h, const void* const* host_pla
     const size_t row_bytes = (size_t)cols * eb;
     const size_t pitch = (row_bytes + 15) & ~(size_t)15;
     const size_t plane_bytes = pitch * rows;
-    const size_t disp_eb = cfg->nxcorr_threshold >= 0 ? 4 : 2;
+    const size_t disp_eb = has_thr(cfg) ? 4 : 2;
     const size_t corr_eb = cfg->precision != 0 ? 8 : 4;
-    const bool want_corr = host_corrmap && cfg->nxcorr_threshold >= 0;
+    const bool want_corr = host_corrmap && has_thr(cfg);
     const int band_rows_max = (rows + bands - 1) / bands + 1;
     {
         // reserve everything up front: a reallocation inside the pipeline would stall it
@@ -647,7 +652,7 @@ int bicos_b200_match_host_begin(bicos_b200_handle h, const void* const* host_pla
         CU(h->desc0.reserve(dpw * band_rows_max * sizeof(uint32_t)));
         CU(h->desc1.reserve(dpw * band_rows_max * sizeof(uint32_t)));
         CU(h->keys.reserve(px * sizeof(uint32_t) * 4));
-        if (cfg->nxcorr_threshold >= 0 && cfg->subpixel_step >= 0)
+        if (has_thr(cfg) && cfg->subpixel_step >= 0)
             if (int rc = prepare_steps(h, cfg->subpixel_step, h->s_compute))
                 return rc;
     }

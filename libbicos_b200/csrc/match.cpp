@@ -55,6 +55,7 @@ thread_local HandleCache t_handles;
 bicos_b200_config to_c_config(const Config& cfg) {
     bicos_b200_config c {};
     c.nxcorr_threshold = cfg.nxcorr_threshold.value_or(-1.f);
+    c.negative_threshold_is_set = cfg.nxcorr_threshold.has_value() && !(*cfg.nxcorr_threshold >= 0) ? 1 : 0;
     c.subpixel_step = cfg.subpixel_step.value_or(-1.f);
     c.min_variance = cfg.min_variance.value_or(-1.f);
     c.mode = cfg.mode == TransformMode::FULL ? 1 : 0;
@@ -202,7 +203,7 @@ void match(
         cuda_check(cudaSetDevice(device), "cudaSetDevice");
     try {
         disparity.create(v0.rows, v0.cols, bicos_b200_disparity_type(&c));
-        const bool want_corr = corrmap && c.nxcorr_threshold >= 0; // cpu.cpp:77-81
+        const bool want_corr = corrmap && cfg.nxcorr_threshold.has_value(); // cpu.cpp:77-81
         if (want_corr)
             corrmap->create(v0.rows, v0.cols, bicos_b200_corrmap_type(&c));
         const int rc = bicos_b200_match(
@@ -244,7 +245,7 @@ void match_sharded(
 
     cuda_check(cudaSetDevice(home), "cudaSetDevice");
     disparity.create(v0.rows, v0.cols, bicos_b200_disparity_type(&c));
-    const bool want_corr = corrmap && c.nxcorr_threshold >= 0;
+    const bool want_corr = corrmap && cfg.nxcorr_threshold.has_value();
     if (want_corr)
         corrmap->create(v0.rows, v0.cols, bicos_b200_corrmap_type(&c));
     cuda_check(cudaDeviceSynchronize(), "sync home device"); // inputs and outputs visible to the peers

@@ -75,7 +75,7 @@ BicosResult* BICOS_Match(void** stack0_data, int* stack0_rows, int* stack0_cols,
                 || stack1_rows[i] != rows || stack1_cols[i] != cols || (stack1_types[i] & 7) != depth)
                 return fail("images differ in size or type");
 
-        bicos_b200_config cfg;
+        bicos_b200_config cfg {};
         cfg.nxcorr_threshold = config->nxcorr_threshold;
         cfg.subpixel_step = config->subpixel_step;
         cfg.min_variance = config->min_variance;
