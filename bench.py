@@ -296,19 +296,28 @@ def main():
     popc_alg = COLS * px * K  # S = W * P * K popc32 per match
     tr_bytes = 2 * N_IMAGES * px + 2 * px * 4 * K  # T_B = 2 n P b + 2 P D
     re_bytes = 2 * N_IMAGES * px + px * (2 + 4 + 4)  # R_B = 2 n P b + P (2 + 4 + c)
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f)
+    except OSError:
+        pass
+    popc_issued = COLS * px * 3  # the kernel's carry-save form: 3 POPC per 128-bit pair
     roofline = {
         "kernel": "search_kernel<4, CONSISTENCY>", "bound": "popc", "achieved": popc_alg / t_se / 1e12,
-        "peak": popc_peak / 1e12, "unit": "Tpopc32/s", "frac": popc_alg / t_se / popc_peak, "traffic": None,
+        "peak": popc_peak / 1e12, "unit": "Tpopc32/s", "frac": popc_alg / t_se / popc_peak,
+        "pipe_frac": popc_issued / t_se / popc_peak, "traffic": traffic.get("search"),
         "peak_source": popc_src, "ms_per_launch": t_se * 1e3,
-        "note": "algorithmic popc32 (4 words per 128-bit pair); the kernel issues 3 POPC per pair after carry-save "
-                "compression, so frac can exceed the share of POPC-pipe cycles",
+        "note": "frac = algorithmic popc32 (SURVEY 8d: 4 words per 128-bit pair) over the measured POPC issue rate; the "
+                "kernel issues 3 POPC per pair after carry-save compression, so frac exceeds 1 while pipe_frac (issued "
+                "POPC over the same peak; ncu: XU pipe 95.5 % active) is the share of POPC-pipe cycles in use",
     }
     roofline_other = [
         {"kernel": "transform_limited_kernel<u8,4> x2", "bound": "hbm", "achieved": tr_bytes / t_tr / 1e9,
-         "peak": hbm_peak, "unit": "GB/s", "frac": tr_bytes / t_tr / 1e9 / hbm_peak, "traffic": None,
+         "peak": hbm_peak, "unit": "GB/s", "frac": tr_bytes / t_tr / 1e9 / hbm_peak, "traffic": traffic.get("transform"),
          "peak_source": hbm_src, "ms_per_launch": t_tr * 1e3 / 2},
         {"kernel": "refine_kernel<u8,float,subpixel,33>", "bound": "hbm", "achieved": re_bytes / t_re / 1e9,
-         "peak": hbm_peak, "unit": "GB/s", "frac": re_bytes / t_re / 1e9 / hbm_peak, "traffic": None,
+         "peak": hbm_peak, "unit": "GB/s", "frac": re_bytes / t_re / 1e9 / hbm_peak, "traffic": traffic.get("refine"),
          "peak_source": hbm_src, "ms_per_launch": t_re * 1e3,
          "note": "subpixel mode is FP32-issue bound (20 x-steps x n x ~13 flops per pixel), not HBM bound"},
     ]
@@ -322,6 +331,22 @@ def main():
         cpu_baseline = {"value": rows * COLS / t / 1e6, "unit": "Mpx/s", "cores": cores, "kind": kind,
                         "sample": f"{rows} of {ROWS} rows of one stereo stack, {t:.1f} s wall, all host threads"}
 
+    # the reference's own CUDA backend, unmodified, compiled for sm_100a (oracle/_ref/libbicos_refcuda.so):
+    # a second baseline beside the CPU build (BASELINE.json north_star); device-resident inputs
+    reference_cuda = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            import oracle
+
+            if oracle.refcuda.available():
+                l0, r0 = host[0]
+                med, mn = oracle.refcuda.time(l0, r0, warmup=3, iters=9, **CFG)
+                reference_cuda = {"value": px / med / 1e3, "unit": "Mpx/s", "ms_per_match": med, "ms_per_match_min": mn,
+                                  "how": "unmodified reference src/impl/cuda.cu (BICOS_CUDA_HAS_UINT128) built for sm_100a "
+                                         "against oracle/shim; median of 9 individually timed BICOS::match calls"}
+        except Exception as e:  # a baseline must never take the product's numbers down with it
+            reference_cuda = {"unavailable": str(e)}
+
     line = {
         "metric": "Mpx/s disparity", "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "ms_per_match": ms_per_step / FRAMES,
@@ -333,7 +358,7 @@ def main():
                 "api": "bicos_b200_match_host_begin/_end, 2 frames in flight (pinned host stacks -> host disparity + corrmap)"},
         "gpu_launches": launches,
         "stage_ms_per_match": {"transform_x2": t_tr * 1e3, "search": t_se * 1e3, "refine": t_re * 1e3},
-        "roofline": roofline, "roofline_other": roofline_other, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "roofline": roofline, "roofline_other": roofline_other, "cpu_baseline": cpu_baseline, "reference_cuda": reference_cuda, "clocks": clocks,
     }
     print(json.dumps(line))
     if world > 1:

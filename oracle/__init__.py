@@ -246,18 +246,18 @@ class _RefCuda:
             corr = corr_buf
         return disp, corr
 
-    def time(self, stack0, stack1, warmup=3, iters=10, **kw) -> float:
-        """ms per BICOS::match, device-resident inputs, CUDA events around `iters` calls."""
+    def time(self, stack0, stack1, warmup=3, iters=10, **kw):
+        """(median, min) ms per BICOS::match over `iters` individually timed calls, device-resident inputs."""
         s0, s1 = _c(stack0), _c(stack1)
         n, rows, cols = s0.shape
         cfg = self._cfg(**kw)
-        ms = ctypes.c_float(0)
+        med, mn = ctypes.c_float(0), ctypes.c_float(0)
         rc = self.lib.refcuda_time(_p(s0), _p(s1), ctypes.c_int(n), ctypes.c_int(rows), ctypes.c_int(cols),
                                    ctypes.c_int(_depth(s0)), ctypes.byref(cfg), ctypes.c_int(warmup),
-                                   ctypes.c_int(iters), ctypes.byref(ms))
+                                   ctypes.c_int(iters), ctypes.byref(med), ctypes.byref(mn))
         if rc != 0:
             raise RuntimeError(self.lib.refcuda_last_error().decode())
-        return float(ms.value)
+        return float(med.value), float(mn.value)
 
 
 refcuda = _RefCuda(os.path.join(_HERE, "_ref", "libbicos_refcuda.so"))

@@ -16,6 +16,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -100,10 +101,12 @@ int refcuda_match(const void* left, const void* right, int n, int rows, int cols
 }
 
 // Device-resident timing of BICOS::match as a caller sees it (its per-call allocations and
-// host registrations included, as in the reference's own CLI timing, src/cli.cpp:177-205):
-// `iters` back-to-back calls between two CUDA events after `warmup` untimed ones.
+// host registrations included, as in the reference's own CLI timing, src/cli.cpp:177-205).
+// Every call is timed on its own between two CUDA events (the reference's match() ends with
+// cudaFree / cudaHostUnregister, i.e. it is synchronous); the per-call times vary a lot because
+// of those allocations, so both the median and the minimum over `iters` calls are returned.
 int refcuda_time(const void* left, const void* right, int n, int rows, int cols, int depth,
-                 const RefConfig* c, int warmup, int iters, float* ms_per_match) {
+                 const RefConfig* c, int warmup, int iters, float* ms_median, float* ms_min) {
     try {
         auto s0 = upload(left, n, rows, cols, depth);
         auto s1 = upload(right, n, rows, cols, depth);
@@ -115,17 +118,22 @@ int refcuda_time(const void* left, const void* right, int n, int rows, int cols,
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
-        cudaEventRecord(e0, nullptr);
-        for (int i = 0; i < iters; ++i)
+        std::vector<float> times;
+        for (int i = 0; i < iters; ++i) {
+            cudaEventRecord(e0, nullptr);
             BICOS::match(s0, s1, disp, cfg, &corr);
-        cudaEventRecord(e1, nullptr);
-        if (cudaEventSynchronize(e1) != cudaSuccess)
-            throw std::runtime_error(cudaGetErrorString(cudaGetLastError()));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, e0, e1);
+            cudaEventRecord(e1, nullptr);
+            if (cudaEventSynchronize(e1) != cudaSuccess)
+                throw std::runtime_error(cudaGetErrorString(cudaGetLastError()));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            times.push_back(ms);
+        }
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
-        *ms_per_match = ms / (float)iters;
+        std::sort(times.begin(), times.end());
+        *ms_median = times[times.size() / 2];
+        *ms_min = times.front();
         return 0;
     } catch (const std::exception& e) {
         g_error = e.what();

@@ -90,14 +90,15 @@ def main():
             if dt == np.uint16:
                 ln, rn = ln.view(np.uint16), rn.view(np.uint16)
             try:
-                ref_ms = refcuda.time(ln, rn, warmup=2, iters=max(3, args.iters // 2), **kw)
+                ref_ms, ref_min = refcuda.time(ln, rn, warmup=3, iters=max(7, args.iters), **kw)
                 rd, rc = refcuda.match(ln, rn, **kw)
                 got = disp.cpu().numpy()
                 ref_invalid = np.isnan(rd) if rd.dtype.kind == "f" else rd == -32768
                 got_invalid = np.isnan(got) | (got == -32768)
                 both = ~ref_invalid & ~got_invalid
                 line["reference_cuda"] = {
-                    "ms_per_match": ref_ms, "mpx_per_s": px / ref_ms / 1e3, "speedup": ref_ms / med,
+                    "ms_per_match": ref_ms, "ms_min": ref_min, "mpx_per_s": px / ref_ms / 1e3,
+                    "speedup": ref_ms / med, "speedup_vs_ref_min": ref_min / mn,
                     "valid_mask_mismatch": int((ref_invalid != got_invalid).sum()),
                     "disparity_mismatch_gt_1e-3": int((np.abs(rd.astype(np.float64)[both] - got[both]) > 1e-3).sum()),
                     "pixels": int(px),
