@@ -276,12 +276,27 @@ __global__ void __launch_bounds__(THREADS) transform_full_kernel(
 // Runtime n: bits of t >= n-2 are masked off afterwards and the 4 tail bits are inserted at
 // their runtime position, exactly as in describe_limited().
 
-__device__ __forceinline__ uint32_t lt_u8x4(uint32_t a_nlo, uint32_t a, uint32_t b_lo, uint32_t b) {
+// x * m + y with m a kernel parameter equal to 1 (or -1): an integer add that ptxas must emit as
+// IMAD, i.e. on the FMA pipe. ncu showed this kernel bound by the ALU pipe (LOP3 / SHF / IADD3 /
+// PRMT, 91 % busy) with the FMA pipe at 10 %: steering the adds over halves the ALU work.
+__device__ __forceinline__ uint32_t fma_add(uint32_t x, uint32_t m, uint32_t y) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(m), "r"(y));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t lt_u8x4(uint32_t a_nlo, uint32_t a, uint32_t b_lo, uint32_t b, uint32_t one) {
     // bit 7 of every byte: a < b. a_nlo = ~a & 0x7f.., b_lo = b & 0x7f..
     uint32_t r;
-    const uint32_t t = b_lo + a_nlo; // per byte <= 254: no carry across lanes
+    const uint32_t t = fma_add(b_lo, one, a_nlo); // per byte <= 254: no carry across lanes
     asm("lop3.b32 %0, %1, %2, %3, 0xb2;" : "=r"(r) : "r"(b), "r"(a), "r"(t)); // maj(b, ~a, t)
     return r;
+}
+
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
 }
 
 template<int K>
@@ -291,7 +306,9 @@ __global__ void __launch_bounds__(THREADS) transform_limited_u8x4_kernel(
     int cols,
     size_t in_pitch,
     uint32_t* __restrict__ desc,
-    size_t desc_pitch_words
+    size_t desc_pitch_words,
+    uint32_t one, // 1 and -1 as run-time values, see fma_add()
+    uint32_t minus_one
 ) {
     constexpr int NB = 8 * K + 1;
     constexpr uint32_t LO7 = 0x7F7F7F7Fu, H16 = 0x80008000u, B16 = 0x00FF00FFu;
@@ -318,8 +335,8 @@ __global__ void __launch_bounds__(THREADS) transform_limited_u8x4_kernel(
     uint32_t se = 0u, so = 0u;
 #pragma unroll
     for (int t = 0; t < NB; ++t) {
-        se += raw[t] & B16;
-        so += (raw[t] >> 8) & B16;
+        se = fma_add(raw[t] & B16, one, se);
+        so = fma_add((raw[t] >> 8) & B16, one, so);
     }
     // thr = ceil(sum / n) per pixel: p*n < sum  <=>  p < thr. Exact reciprocal multiply:
     // floor(x/n) == (x*m) >> 24 with m = ceil(2^24/n) for x < 2^15, n <= 65.
@@ -340,14 +357,16 @@ __global__ void __launch_bounds__(THREADS) transform_limited_u8x4_kernel(
         const int sh = 7 - (pos & 7);
         acc[pos >> 3] |= (r >> sh) & (0x01010101u << (pos & 7));
     };
-    // 16-bit-lane results (bit15/31 CLEAR means "less"): even word -> bytes 0,2; odd -> bytes 1,3
+    // 16-bit-lane results (sign bit CLEAR means "less"; even word = pixels 0,2, odd word = pixels
+    // 1,3): one PRMT in sign-replication mode gathers the four sign bits as 0x00 / 0xFF bytes in
+    // pixel order, one LOP3 drops the complement into the bit position
     auto put16 = [&](int pos, uint32_t de, uint32_t dod) {
-        acc[pos >> 3] |= (~de >> (15 - (pos & 7))) & (0x00010001u << (pos & 7));
-        acc[pos >> 3] |= (~dod >> (7 - (pos & 7))) & (0x01000100u << (pos & 7));
+        const uint32_t ge = prmt_b32(de, dod, 0xFBD9u); // byte j = 0xFF iff NOT less for pixel j
+        acc[pos >> 3] |= ~ge & (0x01010101u << (pos & 7));
     };
 
     uint32_t lo_next = raw[0] & LO7, lo_next2 = raw[1] & LO7; // (b & 0x7f) of p[t+1], p[t+2]
-    uint32_t pe_prev2 = 0u, po_prev2 = 0u, pe_prev1 = 0u, po_prev1 = 0u; // ps(t-2), ps(t-1)
+    uint32_t pe_prev2 = 0u, po_prev2 = 0u, pe_prev1 = 0u, po_prev1 = 0u; // ps(t-2) + 0x8000, ps(t-1) + 0x8000
     uint32_t e_cur = raw[0] & B16, o_cur = (raw[0] >> 8) & B16;
 #pragma unroll
     for (int t = 0; t < NB - 2; ++t) {
@@ -359,26 +378,26 @@ __global__ void __launch_bounds__(THREADS) transform_limited_u8x4_kernel(
         lo_next = b_lo;
         lo_next2 = c_lo;
         const uint32_t a_nlo = a_lo ^ LO7;
-        put8(base + 0, lt_u8x4(a_nlo, a, b_lo, b)); // p[t] < p[t+1]
-        put8(base + 1, lt_u8x4(a_nlo, a, c_lo, c)); // p[t] < p[t+2]
-        put8(base + 2, lt_u8x4(a_nlo, a, thr_lo, thr)); // p[t]*n < sum
+        put8(base + 0, lt_u8x4(a_nlo, a, b_lo, b, one)); // p[t] < p[t+1]
+        put8(base + 1, lt_u8x4(a_nlo, a, c_lo, c, one)); // p[t] < p[t+2]
+        put8(base + 2, lt_u8x4(a_nlo, a, thr_lo, thr, one)); // p[t]*n < sum
         const uint32_t e_nxt = b & B16, o_nxt = (b >> 8) & B16;
-        const uint32_t pe = e_cur + e_nxt, po = o_cur + o_nxt; // ps(t) in 16-bit lanes, <= 510
-        if (t >= 2) // ps(t-2) < ps(t): bit 15 of (x | 0x8000) - y stays set iff x >= y
-            put16(base + 3, (pe_prev2 | H16) - pe, (po_prev2 | H16) - po);
+        const uint32_t pe = fma_add(e_cur, one, e_nxt), po = fma_add(o_cur, one, o_nxt); // ps(t), 16-bit lanes, <= 510
+        if (t >= 2) // ps(t-2) < ps(t): the sign bit of ps(t-2) + 0x8000 - ps(t) stays set iff ps(t-2) >= ps(t)
+            put16(base + 3, fma_add(pe, minus_one, pe_prev2), fma_add(po, minus_one, po_prev2));
         pe_prev2 = pe_prev1;
         po_prev2 = po_prev1;
-        pe_prev1 = pe;
-        po_prev1 = po;
+        pe_prev1 = fma_add(pe, one, H16);
+        po_prev1 = fma_add(po, one, H16);
         e_cur = e_nxt;
         o_cur = o_nxt;
     }
 
     // tail bits (descriptor_transform.hpp:62-69), per pixel lanes
     const uint32_t ta_nlo = (ta & LO7) ^ LO7;
-    const uint32_t r0 = lt_u8x4(ta_nlo, ta, tb & LO7, tb);
-    const uint32_t r1 = lt_u8x4(ta_nlo, ta, thr_lo, thr);
-    const uint32_t r2 = lt_u8x4((tb & LO7) ^ LO7, tb, thr_lo, thr);
+    const uint32_t r0 = lt_u8x4(ta_nlo, ta, tb & LO7, tb, one);
+    const uint32_t r1 = lt_u8x4(ta_nlo, ta, thr_lo, thr, one);
+    const uint32_t r2 = lt_u8x4((tb & LO7) ^ LO7, tb, thr_lo, thr, one);
     const uint32_t ab_e = (ta & B16) + (tb & B16), ab_o = ((ta >> 8) & B16) + ((tb >> 8) & B16);
     const uint32_t pv_e = (tpa & B16) + (tpb & B16), pv_o = ((tpa >> 8) & B16) + ((tpb >> 8) & B16);
     // n < 4: the previous pair sum is -1, the bit is always set
@@ -394,6 +413,20 @@ __global__ void __launch_bounds__(THREADS) transform_limited_u8x4_kernel(
         keep_mask[k] = keep <= 0 ? 0u : keep >= 32 ? 0xFFFFFFFFu : ((1u << keep) - 1u);
     }
 
+    // byte j of acc[4k .. 4k+3] -> word k of pixel j: a 4x4 byte transpose per word index, two
+    // PRMT stages (8 instead of 12 permutes)
+    uint32_t words[4][K]; // [pixel][word]
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint32_t a0 = acc[4 * k], a1 = acc[4 * k + 1], a2 = acc[4 * k + 2], a3 = acc[4 * k + 3];
+        const uint32_t t01l = prmt_b32(a0, a1, 0x5140u), t23l = prmt_b32(a2, a3, 0x5140u); // bytes 0,1 of each
+        const uint32_t t01h = prmt_b32(a0, a1, 0x7362u), t23h = prmt_b32(a2, a3, 0x7362u); // bytes 2,3 of each
+        words[0][k] = prmt_b32(t01l, t23l, 0x5410u);
+        words[1][k] = prmt_b32(t01l, t23l, 0x7632u);
+        words[2][k] = prmt_b32(t01h, t23h, 0x5410u);
+        words[3][k] = prmt_b32(t01h, t23h, 0x7632u);
+    }
+
     uint32_t* out = desc + (size_t)row * desc_pitch_words + (size_t)col * K;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -406,10 +439,7 @@ __global__ void __launch_bounds__(THREADS) transform_limited_u8x4_kernel(
             Bits<K> d;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                // bytes j of acc[4k .. 4k+3] -> word k of pixel j
-                const uint32_t lo = __byte_perm(acc[4 * k], acc[4 * k + 1], 0x0040 + 0x11 * j);
-                const uint32_t hi = __byte_perm(acc[4 * k + 2], acc[4 * k + 3], 0x0040 + 0x11 * j);
-                uint32_t v = __byte_perm(lo, hi, 0x5410) & keep_mask[k];
+                uint32_t v = words[j][k] & keep_mask[k];
                 if (k == word)
                     v |= (uint32_t)ins;
                 if (k == word + 1)
@@ -503,7 +533,7 @@ cudaError_t launch_limited_k(
     const dim3 grid((cols + THREADS * PT - 1) / (THREADS * PT), rows);
     if constexpr (sizeof(TIn) == 1) {
         if (vec_ok) {
-            transform_limited_u8x4_kernel<K><<<grid, THREADS, 0, stream>>>(planes, n, cols, in_pitch, desc, desc_pitch_words);
+            transform_limited_u8x4_kernel<K><<<grid, THREADS, 0, stream>>>(planes, n, cols, in_pitch, desc, desc_pitch_words, 1u, 0xFFFFFFFFu);
             return cudaGetLastError();
         }
     }

@@ -199,6 +199,33 @@ def test_match_against_unmodified_reference(handle, oracles):
         assert _same(corr.cpu().numpy(), want_c)
 
 
+def test_double_precision_against_reference_cuda_build(handle, oracles):
+    """Pins the double-precision NXC (which the reference's CPU build does not have) against the
+    reference's own CUDA backend, compiled unmodified for sm_100a (oracle/_ref/libbicos_refcuda.so):
+    same valid mask, correlation within 1e-12 wherever the reference evaluated it. Integer mode:
+    the reference's CUDA build contracts the subpixel polynomial, so subpixel results are not
+    comparable bit for bit (covered against the CPU oracle instead)."""
+    import oracle
+
+    if not oracle.refcuda.available():
+        pytest.skip("oracle/_ref/libbicos_refcuda.so not present (make -C oracle refcuda)")
+    for n, dtype, kw in ((33, np.uint8, dict(nxcorr_threshold=0.9, min_variance=2.0, double=True)),
+                         (16, np.uint16, dict(nxcorr_threshold=0.9, mode_full=True, double=True, consistency=True))):
+        left, right, _ = synth.make_stacks(n, 512, 384, dtype, seed=41, row0=200, rows=64)
+        ref_d, ref_c = oracle.refcuda.match(left, right, **kw)
+        disp, corr = handle.match(_cuda(left), _cuda(right), Config(**kw))
+        got_d, got_c = disp.cpu().numpy(), corr.cpu().numpy()
+        assert ref_d.dtype == np.int16 and ref_c.dtype == np.float64 and got_c.dtype == np.float64
+        valid_ref = ref_d != -32768
+        valid_got = got_d != -32768
+        assert np.array_equal(valid_ref, valid_got)
+        assert np.array_equal(ref_d[valid_ref].astype(np.float32), got_d[valid_got])
+        # the reference leaves corrmap cells it never evaluated uninitialised: compare where we evaluated
+        ev = ~np.isnan(got_c)
+        assert ev.sum() > 0.5 * ev.size
+        assert np.max(np.abs(ref_c[ev] - got_c[ev])) <= 1e-12
+
+
 def test_match_host_and_rows(handle, oracles):
     """Host-buffer entry point and the row-sharded entry point give the same answer."""
     import torch
