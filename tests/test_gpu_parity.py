@@ -186,6 +186,48 @@ def test_match_double_parity(handle, oracles, n, dtype, rows, cols, kw):
     assert np.max(np.abs(got_d[both] - want_d[both]), initial=0) <= 1e-3
 
 
+@pytest.mark.parametrize("rows,cols", [(1, 1), (1, 2), (2, 3), (3, 31), (1, 129), (2, 513), (1, 1025)])
+def test_tiny_and_ragged_images(handle, oracles, rows, cols):
+    """Degenerate sizes: single pixels, single rows, widths just past a unit / chunk boundary."""
+    n = 9
+    left, right, _ = synth.make_stacks(n, 64, max(cols, 8), np.uint8, seed=rows * 100 + cols, rows=rows)
+    left, right = np.ascontiguousarray(left[:, :, :cols]), np.ascontiguousarray(right[:, :, :cols])
+    for kw in (dict(nxcorr_threshold=None), dict(nxcorr_threshold=0.5, consistency=True, max_lr_diff=1, no_dupes=True),
+               dict(nxcorr_threshold=0.3, subpixel_step=0.5, min_variance=0.5)):
+        want_d, want_c = oracles.port.match(left, right, **kw)
+        disp, corr = handle.match(_cuda(left), _cuda(right), Config(**kw))
+        assert _same(disp.cpu().numpy(), want_d), (rows, cols, kw)
+        if want_c is not None:
+            assert _same(corr.cpu().numpy(), want_c), (rows, cols, kw)
+
+
+@pytest.mark.parametrize("k,cols,flags", [(8, 4100, 3), (4, 4100, 2), (1, 9000, 1), (2, 2050, 3)])
+def test_search_wide_rows_split_units(handle, oracles, k, cols, flags):
+    """Wide rows: several chunks per unit and up to 8 CTAs per unit merged by atomicMin."""
+    import torch
+
+    rng = np.random.default_rng(k * 7 + cols)
+    rows = 3
+    d0 = _random_desc(rng, rows, cols, k, 6)
+    d1 = _random_desc(rng, rows, cols, k, 6)
+    src = rng.integers(0, cols, size=cols // 2)
+    dst = rng.integers(0, cols, size=cols // 2)
+    d0[:, dst] = d1[:, src]
+    want = oracles.port.bicos(d0, d1, flags, 2)
+    pitch = (cols * k + 3) // 4 * 4
+
+    def pitched(d):
+        buf = np.zeros((rows, pitch), dtype=np.uint32)
+        buf[:, : cols * k] = d.reshape(rows, cols * k)
+        return torch.from_numpy(buf.view(np.int32)).cuda()
+
+    keys = handle.search(pitched(d0), pitched(d1), k, cols, flags)
+    dummy = torch.zeros((2, rows, cols), dtype=torch.uint8, device="cuda")
+    cfg = Config(nxcorr_threshold=None, consistency=bool(flags & FLAG_CONSISTENCY), max_lr_diff=2, no_dupes=flags == 3)
+    disp, _, _ = handle.refine(dummy, dummy, cfg, keys)
+    assert np.array_equal(disp.cpu().numpy(), want)
+
+
 def test_match_against_unmodified_reference(handle, oracles):
     """Same comparison, but against the compiled reference sources themselves (when they travelled)."""
     if not oracles.ref.available():
