@@ -228,6 +228,40 @@ def test_search_wide_rows_split_units(handle, oracles, k, cols, flags):
     assert np.array_equal(disp.cpu().numpy(), want)
 
 
+def test_randomised_configurations(handle, oracles):
+    """Seeded sweep over stack sizes, depths, modes, variants, steps and image shapes: every
+    dispatch branch (descriptor width, unit size A, split count, full / partial stacks, packed and
+    scalar subpixel paths, odd step counts) against the oracle, bit for bit."""
+    rng = np.random.default_rng(20261018)
+    checked = 0
+    for trial in range(48):
+        full = bool(rng.integers(0, 2)) and trial % 3 == 0
+        n = int(rng.integers(2, 17)) if full else int(rng.choice([2, 3, 4, 5, 8, 9, 10, 16, 17, 18, 25, 32, 33, 34, 48, 64, 65]))
+        dtype = np.uint16 if rng.integers(0, 2) else np.uint8
+        rows, cols = int(rng.integers(1, 12)), int(rng.choice([17, 64, 100, 255, 256, 300, 513, 640, 777, 1100]))
+        kw = dict(mode_full=full)
+        kind = trial % 4
+        if kind == 0:
+            kw.update(nxcorr_threshold=None)
+        else:
+            kw.update(nxcorr_threshold=float(rng.choice([0.3, 0.7, 0.9, 0.96])))
+            if rng.integers(0, 2):
+                kw.update(min_variance=float(rng.choice([0.0, 1.0, 4.0])))
+            if kind >= 2:
+                kw.update(subpixel_step=float(rng.choice([0.1, 0.125, 0.2, 0.3, 0.4, 0.5, 0.7, 1.0])))
+        if rng.integers(0, 2):
+            kw.update(consistency=True, max_lr_diff=int(rng.integers(0, 4)), no_dupes=bool(rng.integers(0, 2)))
+        double = kind == 3 and bool(rng.integers(0, 2))
+        left, right, _ = synth.make_stacks(n, 256, cols, dtype, seed=1000 + trial, row0=int(rng.integers(0, 200)), rows=rows)
+        want_d, want_c = oracles.port.match(left, right, double=double, **kw)
+        disp, corr = handle.match(_cuda(left), _cuda(right), Config(double=double, **kw))
+        assert _same(disp.cpu().numpy(), want_d), (trial, n, dtype, rows, cols, kw, double)
+        if want_c is not None:
+            assert _same(corr.cpu().numpy(), want_c), (trial, n, dtype, rows, cols, kw, double)
+        checked += 1
+    assert checked == 48
+
+
 def test_match_against_unmodified_reference(handle, oracles):
     """Same comparison, but against the compiled reference sources themselves (when they travelled)."""
     if not oracles.ref.available():
