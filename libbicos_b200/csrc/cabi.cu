@@ -11,11 +11,15 @@
 #include "kernels.cuh"
 
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace bicos_b200;
@@ -73,6 +77,124 @@ struct DeviceBuffer {
     }
 };
 
+struct PinnedBuffer {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap)
+            return cudaSuccess;
+        release();
+        cudaError_t err = cudaHostAlloc(&ptr, bytes, cudaHostAllocDefault);
+        if (err == cudaSuccess)
+            cap = bytes;
+        else
+            ptr = nullptr;
+        return err;
+    }
+    void release() {
+        if (ptr)
+            cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+// A few persistent host threads for memcpy between pageable caller memory and the pinned staging
+// buffers of the host-buffer entry points (one thread moves ~10 GB/s, PCIe wants 50).
+class CopyPool {
+public:
+    static CopyPool& get() {
+        static CopyPool pool;
+        return pool;
+    }
+    // fn(i) for i in [0, count), spread over the workers and the calling thread; returns when all ran
+    void parallel_for(int count, const std::function<void(int)>& fn) {
+        if (count <= 0)
+            return;
+        std::unique_lock<std::mutex> call_lock(call_mutex_); // one job at a time
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            job_ = &fn;
+            next_ = 0;
+            count_ = count;
+            pending_ = count;
+            ++generation_;
+        }
+        cv_.notify_all();
+        run_some();
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [&] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+private:
+    CopyPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        int n = hw >= 16 ? 7 : hw >= 8 ? 3 : 1; // plus the calling thread
+        for (int i = 0; i < n; ++i)
+            workers_.emplace_back([this] { worker(); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t: workers_)
+            t.join();
+    }
+    void run_some() {
+        for (;;) {
+            int i;
+            const std::function<void(int)>* fn;
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (!job_ || next_ >= count_)
+                    return;
+                i = next_++;
+                fn = job_;
+            }
+            (*fn)(i);
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0)
+                    cv_done_.notify_all();
+            }
+        }
+    }
+    void worker() {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+                if (stop_)
+                    return;
+                seen = generation_;
+            }
+            run_some();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_, call_mutex_;
+    std::condition_variable cv_, cv_done_;
+    const std::function<void(int)>* job_ = nullptr;
+    int next_ = 0, count_ = 0, pending_ = 0;
+    unsigned long long generation_ = 0;
+    bool stop_ = false;
+};
+
+// pageable (unregistered) host memory? Pinned and registered memory can be handed to the DMA
+// engines directly; everything else goes through the handle's pinned staging buffers.
+bool is_pageable(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;
@@ -117,6 +239,7 @@ size_t depth_bytes(int depth) {
 } // namespace
 
 constexpr int MAX_BANDS = 8;
+constexpr int PIN_SLOTS = 3;
 constexpr int N_STAGES = 3; // transform (both stacks), search, refine
 
 struct bicos_b200_handle_s {
@@ -126,6 +249,11 @@ struct bicos_b200_handle_s {
     float xs_step = -1.f;
     int xs_count = 0;
     bool host_pending = false; // between bicos_b200_match_host_begin and _end
+    // pageable callers: ring of pinned band buffers for the inputs, pinned images for the outputs
+    PinnedBuffer pin_in[PIN_SLOTS], pin_disp, pin_corr;
+    cudaEvent_t ev_slot[PIN_SLOTS] = {};
+    void *user_disp = nullptr, *user_corr = nullptr; // where _end copies the pinned outputs to
+    size_t user_disp_bytes = 0, user_corr_bytes = 0;
     long long launches = 0;
     // host-buffer pipeline (bicos_b200_match_host): upload / compute / download streams
     cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
@@ -434,6 +562,13 @@ int bicos_b200_destroy(bicos_b200_handle h) {
             b->release();
         for (cudaEvent_t e: h->prof_events)
             cudaEventDestroy(e);
+        for (int k = 0; k < PIN_SLOTS; ++k) {
+            h->pin_in[k].release();
+            if (h->ev_slot[k])
+                cudaEventDestroy(h->ev_slot[k]);
+        }
+        h->pin_disp.release();
+        h->pin_corr.release();
         for (int b = 0; b < MAX_BANDS; ++b) {
             if (h->ev_in[b])
                 cudaEventDestroy(h->ev_in[b]);
@@ -666,13 +801,55 @@ int bicos_b200_match_host_begin(bicos_b200_handle h, const void* const* host_pla
     const bool contig0 = planes_contiguous(host_planes0, n, row_bytes * rows);
     const bool contig1 = planes_contiguous(host_planes1, n, row_bytes * rows);
 
+    // Pageable caller memory (numpy arrays, malloc: what pybicos' BICOS_Match passes) cannot be
+    // handed to the DMA engines; the driver would stage it through a small bounce buffer at about
+    // 8 GB/s. Instead a few host threads copy band b into a ring of pinned band buffers while the
+    // GPU works on band b-1, and the results come back through pinned images that _end copies out.
+    const bool stage_inputs = is_pageable(host_planes0[0]) || is_pageable(host_planes1[0]);
+    const bool stage_disp = is_pageable(host_disparity);
+    const bool stage_corr = want_corr && is_pageable(host_corrmap);
+    const size_t slot_plane = row_bytes * band_rows_max; // one plane's band, dense
+    if (stage_inputs)
+        for (int k = 0; k < PIN_SLOTS; ++k) {
+            CU(h->pin_in[k].reserve(slot_plane * 2 * n));
+            if (!h->ev_slot[k])
+                CU(cudaEventCreateWithFlags(&h->ev_slot[k], cudaEventDisableTiming | cudaEventBlockingSync));
+        }
+    if (stage_disp)
+        CU(h->pin_disp.reserve((size_t)rows * cols * disp_eb));
+    if (stage_corr)
+        CU(h->pin_corr.reserve((size_t)rows * cols * corr_eb));
+    char* const out_disp = static_cast<char*>(stage_disp ? h->pin_disp.ptr : host_disparity);
+    char* const out_corr = static_cast<char*>(stage_corr ? h->pin_corr.ptr : host_corrmap);
+
     // upload of band b is enqueued right before the match of band b, so the host never runs
     // far ahead of the device with copy submissions while kernels wait to be launched
     auto enqueue = [&]() -> int {
         for (int b = 0; b < bands; ++b) {
             const int rb = (int)((long long)rows * b / bands), re = (int)((long long)rows * (b + 1) / bands);
-            CU(upload_band(host_planes0, contig0, base, n, rows, row_bytes, pitch, rb, re, h->s_in));
-            CU(upload_band(host_planes1, contig1, base + plane_bytes * n, n, rows, row_bytes, pitch, rb, re, h->s_in));
+            if (stage_inputs) {
+                const int slot = b % PIN_SLOTS;
+                if (b >= PIN_SLOTS)
+                    CU(cudaEventSynchronize(h->ev_slot[slot])); // its previous upload has left the buffer
+                char* const pin = static_cast<char*>(h->pin_in[slot].ptr);
+                const size_t band_bytes = row_bytes * (size_t)(re - rb);
+                CopyPool::get().parallel_for(2 * n, [&](int i) {
+                    const void* const* planes = i < n ? host_planes0 : host_planes1;
+                    std::memcpy(pin + slot_plane * i, static_cast<const char*>(planes[i % n]) + row_bytes * rb, band_bytes);
+                });
+                // pinned slot [2n][band rows][row_bytes] -> device planes [2n][rows][pitch], rows rb..re
+                cudaMemcpy3DParms cp {};
+                cp.srcPtr = make_cudaPitchedPtr(pin, row_bytes, row_bytes, (size_t)band_rows_max);
+                cp.dstPtr = make_cudaPitchedPtr(base, pitch, row_bytes, (size_t)rows);
+                cp.dstPos = make_cudaPos(0, (size_t)rb, 0);
+                cp.extent = make_cudaExtent(row_bytes, (size_t)(re - rb), (size_t)(2 * n));
+                cp.kind = cudaMemcpyHostToDevice;
+                CU(cudaMemcpy3DAsync(&cp, h->s_in));
+                CU(cudaEventRecord(h->ev_slot[slot], h->s_in));
+            } else {
+                CU(upload_band(host_planes0, contig0, base, n, rows, row_bytes, pitch, rb, re, h->s_in));
+                CU(upload_band(host_planes1, contig1, base + plane_bytes * n, n, rows, row_bytes, pitch, rb, re, h->s_in));
+            }
             CU(cudaEventRecord(h->ev_in[b], h->s_in));
             CU(cudaStreamWaitEvent(h->s_compute, h->ev_in[b], 0));
             if (int rc = do_match(h, dev0.data(), dev1.data(), n, rows, cols, pitch, depth, cfg, rb, re,
@@ -682,13 +859,11 @@ int bicos_b200_match_host_begin(bicos_b200_handle h, const void* const* host_pla
             CU(cudaEventRecord(h->ev_done[b], h->s_compute));
             CU(cudaStreamWaitEvent(h->s_out, h->ev_done[b], 0));
             const size_t off = (size_t)rb * cols, cnt = (size_t)(re - rb) * cols;
-            CU(cudaMemcpyAsync(static_cast<char*>(host_disparity) + off * disp_eb,
-                               static_cast<char*>(h->stage_disp.ptr) + off * disp_eb, cnt * disp_eb,
-                               cudaMemcpyDeviceToHost, h->s_out));
+            CU(cudaMemcpyAsync(out_disp + off * disp_eb, static_cast<char*>(h->stage_disp.ptr) + off * disp_eb,
+                               cnt * disp_eb, cudaMemcpyDeviceToHost, h->s_out));
             if (want_corr)
-                CU(cudaMemcpyAsync(static_cast<char*>(host_corrmap) + off * corr_eb,
-                                   static_cast<char*>(h->stage_corr.ptr) + off * corr_eb, cnt * corr_eb,
-                                   cudaMemcpyDeviceToHost, h->s_out));
+                CU(cudaMemcpyAsync(out_corr + off * corr_eb, static_cast<char*>(h->stage_corr.ptr) + off * corr_eb,
+                                   cnt * corr_eb, cudaMemcpyDeviceToHost, h->s_out));
         }
         return 0;
     };
@@ -698,6 +873,10 @@ int bicos_b200_match_host_begin(bicos_b200_handle h, const void* const* host_pla
         g_error = keep;
         return rc;
     }
+    h->user_disp = stage_disp ? host_disparity : nullptr;
+    h->user_disp_bytes = (size_t)rows * cols * disp_eb;
+    h->user_corr = stage_corr ? host_corrmap : nullptr;
+    h->user_corr_bytes = (size_t)rows * cols * corr_eb;
     h->host_pending = true;
     return 0;
 }
@@ -711,6 +890,22 @@ int bicos_b200_match_host_end(bicos_b200_handle h) {
     h->host_pending = false;
     CU(cudaStreamSynchronize(h->s_out));
     CU(cudaStreamSynchronize(h->s_compute));
+    // pageable result buffers: out of the pinned images, a slice per host thread
+    struct Piece {
+        char* dst;
+        const char* src;
+        size_t bytes;
+    };
+    std::vector<Piece> pieces;
+    auto add = [&](void* user, const PinnedBuffer& pin, size_t bytes) {
+        const size_t step = 1u << 20;
+        for (size_t o = 0; user && o < bytes; o += step)
+            pieces.push_back({ static_cast<char*>(user) + o, static_cast<const char*>(pin.ptr) + o, bytes - o < step ? bytes - o : step });
+    };
+    add(h->user_disp, h->pin_disp, h->user_disp_bytes);
+    add(h->user_corr, h->pin_corr, h->user_corr_bytes);
+    CopyPool::get().parallel_for((int)pieces.size(), [&](int i) { std::memcpy(pieces[i].dst, pieces[i].src, pieces[i].bytes); });
+    h->user_disp = h->user_corr = nullptr;
     return 0;
 }
 

@@ -25,6 +25,53 @@ BicosResult* fail(const std::string& msg) {
 
 } // namespace
 
+// Result images are tens of megabytes: a fresh malloc is a fresh mmap whose pages fault in while
+// the result is copied out, and free() unmaps them again. The Python side copies and frees every
+// result right away (pybicos/__init__.py:237-243), so the last few buffers are kept for reuse.
+namespace {
+struct CachedBuffer {
+    void* ptr;
+    size_t bytes;
+};
+std::mutex g_cache_mutex;
+std::vector<CachedBuffer> g_cache; // free buffers
+std::vector<CachedBuffer> g_live; // handed out, with their sizes
+constexpr size_t CACHE_SLOTS = 4;
+
+void* result_alloc(size_t bytes) {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    void* p = nullptr;
+    for (size_t i = 0; i < g_cache.size(); ++i)
+        if (g_cache[i].bytes == bytes) {
+            p = g_cache[i].ptr;
+            g_cache.erase(g_cache.begin() + (long)i);
+            break;
+        }
+    if (!p)
+        p = std::malloc(bytes);
+    if (p)
+        g_live.push_back({ p, bytes });
+    return p;
+}
+
+void result_free(void* p) {
+    if (!p)
+        return;
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    size_t bytes = 0;
+    for (size_t i = 0; i < g_live.size(); ++i)
+        if (g_live[i].ptr == p) {
+            bytes = g_live[i].bytes;
+            g_live.erase(g_live.begin() + (long)i);
+            break;
+        }
+    if (bytes >= (1u << 20) && g_cache.size() < CACHE_SLOTS)
+        g_cache.push_back({ p, bytes });
+    else
+        std::free(p);
+}
+} // namespace
+
 extern "C" {
 
 const char* BICOS_LastError(void) {
@@ -53,8 +100,8 @@ void BICOS_FreeConfig(BicosConfig* config) {
 void BICOS_FreeResult(BicosResult* result) {
     if (!result)
         return;
-    std::free(result->disparity_data);
-    std::free(result->corrmap_data);
+    result_free(result->disparity_data);
+    result_free(result->corrmap_data);
     delete result;
 }
 
@@ -94,8 +141,8 @@ BicosResult* BICOS_Match(void** stack0_data, int* stack0_rows, int* stack0_cols,
         BicosResult* res = new (std::nothrow) BicosResult();
         if (!res)
             return fail("out of memory");
-        res->disparity_data = std::malloc(disp_bytes ? disp_bytes : 1);
-        res->corrmap_data = corr_bytes ? std::malloc(corr_bytes) : nullptr;
+        res->disparity_data = result_alloc(disp_bytes ? disp_bytes : 1);
+        res->corrmap_data = corr_bytes ? result_alloc(corr_bytes) : nullptr;
         if (!res->disparity_data || (corr_bytes && !res->corrmap_data)) {
             BICOS_FreeResult(res);
             return fail("out of memory");

@@ -93,7 +93,7 @@ class Config:
 
     def __del__(self):
         c, self._c = getattr(self, "_c", None), None
-        if c:
+        if c and _lib is not None:  # module globals are already gone at interpreter shutdown
             _lib.BICOS_FreeConfig(c)
 
     @property
