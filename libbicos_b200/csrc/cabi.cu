@@ -14,6 +14,7 @@
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -238,7 +239,7 @@ size_t depth_bytes(int depth) {
 
 } // namespace
 
-constexpr int MAX_BANDS = 8;
+constexpr int MAX_BANDS = 16;
 constexpr int PIN_SLOTS = 3;
 constexpr int N_STAGES = 3; // transform (both stacks), search, refine
 
@@ -763,7 +764,7 @@ int bicos_b200_match_host_begin(bicos_b200_handle h, const void* const* host_pla
             CU(cudaEventCreateWithFlags(&h->ev_done[b], cudaEventDisableTiming));
         }
     }
-    int bands = rows / 192;
+    int bands = rows / 192; // measured best at 2048 columns (96 .. 768 rows per band tried)
     bands = bands < 1 ? 1 : bands > MAX_BANDS ? MAX_BANDS : bands;
 
     const size_t eb = depth_bytes(depth);
