@@ -183,11 +183,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--table", action="store_true",
+                    help="instead of the bench line: every BASELINE config (tools/bench_configs.py) with the "
+                         "reference's CUDA backend timed beside it, one JSON line per config")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     if args.impl == "reference":
         run_reference_arm(args)
+        return
+    if args.table:
+        import oracle  # baselines are timed beside the product, never inside it
+        from tools import bench_configs
+
+        bench_configs.run_table(["C1", "C2", "metric", "C3", "C4", "C5"], 10,
+                                oracle.refcuda if oracle.refcuda.available() else None)
         return
 
     import numpy as np

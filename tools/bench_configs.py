@@ -1,14 +1,12 @@
-"""Every BASELINE.json config on one B200: the new kernels next to the reference's own CUDA build.
+"""Every BASELINE.json config on one B200. Prints one JSON line per config: device-resident ms
+per match (CUDA events, median of `--iters` after 3 warm-ups), Mpx/s and per-stage times.
 
-Prints one JSON line per config: device-resident ms per match (CUDA events, median of `--iters`
-after 3 warm-ups), Mpx/s, per-stage times, and -- when oracle/_ref/libbicos_refcuda.so travelled
-to the box (`make -C oracle refcuda` in the build container) -- the UNMODIFIED reference CUDA
-backend (reference src/impl/cuda.cu, compiled for sm_100a) timed on the same synthetic stacks,
-plus how many disparities differ between the two (the reference's CUDA build contracts the
-interpolation into FMAs and leaves unevaluated corrmap cells uninitialised, so only the integer
-part is expected to agree everywhere).
-
-bench.py is the contract; this is the per-config table behind DESIGN.md section 4.
+`python bench.py --table` runs the same table with the reference's own CUDA backend timed beside
+every config (bench.py is the one measurement script that may load the baselines under oracle/):
+the UNMODIFIED reference src/impl/cuda.cu compiled for sm_100a (`make -C oracle refcuda`), on the
+same synthetic stacks, plus how many disparities differ between the two (the reference's CUDA
+build contracts the interpolation into FMAs and leaves unevaluated corrmap cells uninitialised,
+so only the integer part is expected to agree everywhere).
 """
 import argparse
 import json
@@ -52,28 +50,16 @@ def median_ms(fn, iters, warmup=3):
     return float(np.median(ts)), float(np.min(ts))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="C1,C2,metric,C3,C4,C5")
-    ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--no-ref", action="store_true")
-    args = ap.parse_args()
-
-    refcuda = None
-    if not args.no_ref:
-        import oracle  # the reference CUDA build is a baseline, timed beside the product, never inside it
-
-        if oracle.refcuda.available():
-            refcuda = oracle.refcuda
-
+def run_table(configs, iters=10, refcuda=None):
+    """`refcuda`: an object with time(l, r, ...) / match(l, r, ...) of the reference CUDA backend, or None."""
     h = lb.Handle(0)
-    for name in args.configs.split(","):
+    for name in configs:
         n, dt, rows, cols, kw, note = CONFIGS[name]
         l, r, _ = synth.make_stacks(n, rows, cols, dt, xp=torch, device="cuda")
         cfg = lb.Config(**kw)
         out = h.match(l, r, cfg)
         h.set_profiling(True)
-        med, mn = median_ms(lambda: h.match(l, r, cfg, out=out), args.iters)
+        med, mn = median_ms(lambda: h.match(l, r, cfg, out=out), iters)
         stage_ms, cnt = h.stage_times()
         h.set_profiling(False)
         px = rows * cols
@@ -90,7 +76,7 @@ def main():
             if dt == np.uint16:
                 ln, rn = ln.view(np.uint16), rn.view(np.uint16)
             try:
-                ref_ms, ref_min = refcuda.time(ln, rn, warmup=3, iters=max(7, args.iters), **kw)
+                ref_ms, ref_min = refcuda.time(ln, rn, warmup=3, iters=max(7, iters), **kw)
                 rd, rc = refcuda.match(ln, rn, **kw)
                 got = disp.cpu().numpy()
                 ref_invalid = np.isnan(rd) if rd.dtype.kind == "f" else rd == -32768
@@ -108,6 +94,14 @@ def main():
         print(json.dumps(line), flush=True)
         del l, r, out
         torch.cuda.empty_cache()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="C1,C2,metric,C3,C4,C5")
+    ap.add_argument("--iters", type=int, default=10)
+    args = ap.parse_args()
+    run_table(args.configs.split(","), args.iters)
 
 
 if __name__ == "__main__":
