@@ -100,8 +100,8 @@ class ClockSampler:
 
 def bind_to_gpu_cpus(local):
     """Pin this process to the CPUs next to its GPU (NVML's ideal set) before any pinned host
-    buffer is allocated: with 8 ranks uploading 35 GB/s each, staging buffers on the wrong NUMA
-    node halve the end-to-end rate. Returns a short description for the JSON line."""
+    buffer is allocated, so that on a multi-socket host the staging buffers of a rank live on its
+    GPU's NUMA node (no effect on a single-node host). Returns a short description for the JSON line."""
     try:
         import pynvml
         import torch
@@ -276,12 +276,13 @@ def main():
     # two handles = two frames in flight: frame f+1 uploads while frame f is matched and frame
     # f-1 downloads (bicos_b200_match_host_begin / _end); every result is complete in host
     # memory when its step ends
-    hh = [h, lb.Handle(local)]
+    inflight = max(1, min(int(os.environ.get("BICOS_BENCH_INFLIGHT", "2")), FRAMES))
+    hh = [h] + [lb.Handle(local) for _ in range(inflight - 1)]
 
     def e2e_step():
         for f, ((l, r), out) in enumerate(zip(host, host_out)):
-            hh[f % 2].match_host_end()  # the frame this handle carried in the previous round
-            hh[f % 2].match_host_begin(l, r, cfg, out=out)
+            hh[f % inflight].match_host_end()  # the frame this handle carried in the previous round
+            hh[f % inflight].match_host_begin(l, r, cfg, out=out)
         for x in hh:
             x.match_host_end()
 
@@ -368,7 +369,7 @@ def main():
                    "l2": f"inputs larger than L2 ({FRAMES} x 208 MB per step per GPU); no explicit flush"},
         "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": FRAMES * 2 * N_IMAGES * px,
                 "d2h_bytes_per_step": FRAMES * px * 8, "ms_per_step": e2e_ms, "matches_device_path": same, "host_affinity": affinity,
-                "api": "bicos_b200_match_host_begin/_end, 2 frames in flight (pinned host stacks -> host disparity + corrmap)"},
+                "api": f"bicos_b200_match_host_begin/_end, {inflight} frames in flight (pinned host stacks -> host disparity + corrmap)"},
         "gpu_launches": launches,
         "stage_ms_per_match": {"transform_x2": t_tr * 1e3, "search": t_se * 1e3, "refine": t_re * 1e3},
         "roofline": roofline, "roofline_other": roofline_other, "cpu_baseline": cpu_baseline, "reference_cuda": reference_cuda, "clocks": clocks,
