@@ -111,11 +111,23 @@ void suite(int rows, int cols) {
     run<K, 2, 5, 128, 2>("A5 NT128 U2 auto", b, 0);
     run<K, 2, 3, 128, 2>("A3 NT128 U2 auto", b, 0);
     run<K, 2, 4, 128, 3>("A4 NT128 U3 x1", b, 1);
+    if constexpr (K <= 2) {
+        run<K, 2, 8, 128, 2>("A8 NT128 U2 auto", b, 0);
+        run<K, 2, 8, 128, 4>("A8 NT128 U4 auto", b, 0);
+        run<K, 2, 4, 128, 4>("A4 NT128 U4 auto", b, 0);
+        run<K, 2, 8, 64, 2>("A8 NT64 U2 auto", b, 0);
+        run<K, 2, 16, 64, 2>("A16 NT64 U2 auto", b, 0);
+    }
     printf("NODUPES\n");
     run<K, 1, 4, 128, 2>("A4 NT128 U2 x1 (one CTA per unit)", b, 1, true);
     run<K, 1, 4, 128, 2>("A4 NT128 U2 x2", b, 2);
     run<K, 1, 5, 128, 2>("A5 NT128 U2 auto", b, 0);
     run<K, 1, 3, 128, 2>("A3 NT128 U2 auto", b, 0);
+    if constexpr (K <= 2) {
+        run<K, 1, 8, 128, 2>("A8 NT128 U2 auto", b, 0);
+        run<K, 1, 8, 128, 4>("A8 NT128 U4 auto", b, 0);
+        run<K, 1, 16, 64, 2>("A16 NT64 U2 auto", b, 0);
+    }
     printf("CONSISTENCY | NODUPES\n");
     run<K, 3, 4, 128, 2>("A4 NT128 U2 x1 (one CTA per unit)", b, 1, true);
     run<K, 3, 4, 128, 2>("A4 NT128 U2 x2", b, 2);
