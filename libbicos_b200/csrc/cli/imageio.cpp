@@ -221,25 +221,10 @@ GrayImage read_image(const std::string& path, bool& was_colour) {
     return read_png(file, path, was_colour);
 }
 
+#include "colormaps.inc"
+
 void colormap_lut(Colormap map, uint8_t lut[256][3]) {
-    for (int i = 0; i < 256; ++i) {
-        const double x = i / 255.0;
-        double r, g, b;
-        if (map == Colormap::TURBO) {
-            // 5th-order fit of Google's Turbo map
-            r = 0.13572138 + x * (4.61539260 + x * (-42.66032258 + x * (132.13108234 + x * (-152.94239396 + x * 59.28637943))));
-            g = 0.09140261 + x * (2.19418839 + x * (4.84296658 + x * (-14.18503333 + x * (4.27729857 + x * 2.82956604))));
-            b = 0.10667330 + x * (12.64194608 + x * (-60.58204836 + x * (110.36276771 + x * (-89.90310912 + x * 27.34824973))));
-        } else {
-            // 6th-order fit of matplotlib's Viridis map
-            r = 0.2777273272234177 + x * (0.1050930431085774 + x * (-0.3308618287255563 + x * (-4.634230498983486 + x * (6.228269936347081 + x * (4.776384997670288 + x * -5.435455855934631)))));
-            g = 0.005407344544966578 + x * (1.404613529898575 + x * (0.214847559468213 + x * (-5.799100973351585 + x * (14.17993336680509 + x * (-13.74514537774601 + x * 4.645852612178535)))));
-            b = 0.3340998053353061 + x * (1.384590162594685 + x * (0.09509516302823659 + x * (-19.33244095627987 + x * (56.69055260068105 + x * (-65.35303263337234 + x * 26.3124352495832)))));
-        }
-        const double c[3] = { r, g, b };
-        for (int k = 0; k < 3; ++k)
-            lut[i][k] = (uint8_t)std::lround(std::fmin(1.0, std::fmax(0.0, c[k])) * 255.0);
-    }
+    std::memcpy(lut, map == Colormap::TURBO ? LUT_TURBO : LUT_VIRIDIS, 256 * 3);
 }
 
 void write_png_rgb(const std::string& path, int rows, int cols, const std::vector<uint8_t>& rgb) {

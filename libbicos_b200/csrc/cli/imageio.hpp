@@ -25,7 +25,7 @@ GrayImage read_image(const std::string& path, bool& was_colour);
 
 enum class Colormap { TURBO, VIRIDIS };
 
-// 256-entry RGB table (polynomial fits of the Turbo / Viridis maps, visualisation only)
+// 256-entry RGB table (colormaps.inc: OpenCV's COLORMAP_TURBO / COLORMAP_VIRIDIS, tabulated)
 void colormap_lut(Colormap map, uint8_t lut[256][3]);
 
 void write_png_rgb(const std::string& path, int rows, int cols, const std::vector<uint8_t>& rgb);

@@ -35,6 +35,79 @@ def test_cli_argument_errors():
     assert res.returncode == 1 and "bicos-cli:" in res.stderr
 
 
+IOCHK = os.path.join(ROOT, "tests", "cpp", "build", "imageio_check")
+
+
+def _read_with_tool(path, tmp):
+    raw = os.path.join(tmp, "img.raw")
+    res = subprocess.run([IOCHK, "read", path, raw], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    buf = open(raw, "rb").read()
+    rows, cols, bits, colour = np.frombuffer(buf, dtype=np.int32, count=4)
+    data = np.frombuffer(buf, dtype=np.uint16 if bits == 16 else np.uint8, offset=16).reshape(rows, cols)
+    return data, bool(colour)
+
+
+@pytest.mark.parametrize("dtype,ext", [(np.uint8, "png"), (np.uint16, "png"), (np.uint8, "pgm"), (np.uint16, "pgm")])
+def test_image_reader_matches_opencv_grey(tmp_path, dtype, ext):
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, np.iinfo(dtype).max + 1, size=(37, 53)).astype(dtype)
+    path = str(tmp_path / f"a.{ext}")
+    assert cv2.imwrite(path, img)
+    got, colour = _read_with_tool(path, str(tmp_path))
+    assert not colour and got.dtype == dtype and np.array_equal(got, img)
+
+
+def test_image_reader_colour_and_alpha(tmp_path):
+    rng = np.random.default_rng(6)
+    bgr = rng.integers(0, 256, size=(21, 40, 3)).astype(np.uint8)
+    for name, img in (("rgb.png", bgr), ("rgba.png", np.dstack([bgr, np.full((21, 40), 200, np.uint8)]))):
+        path = str(tmp_path / name)
+        assert cv2.imwrite(path, img)
+        got, colour = _read_with_tool(path, str(tmp_path))
+        want = cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)  # the reference reads with IMREAD_GRAYSCALE
+        assert colour and np.abs(got.astype(int) - want.astype(int)).max() <= 1
+
+
+def test_image_writers_round_trip(tmp_path):
+    rng = np.random.default_rng(7)
+    disp = rng.normal(40, 5, size=(30, 44)).astype(np.float32)
+    disp[3:6] = np.nan
+    raw = tmp_path / "d.raw"
+    raw.write_bytes(disp.tobytes())
+    res = subprocess.run([IOCHK, "write", "30", "44", "5", str(raw), str(tmp_path / "out")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    tiff = cv2.imread(str(tmp_path / "out.tiff"), cv2.IMREAD_UNCHANGED)
+    assert tiff.dtype == np.float32 and np.array_equal(tiff, disp, equal_nan=True)
+    png = cv2.imread(str(tmp_path / "out.png"), cv2.IMREAD_UNCHANGED)
+    assert png.shape == (30, 44, 3) and (png[3:6] == 0).all() and (png[10:] != 0).any()
+    # the reference's save_image: min-max normalise the valid pixels to 0..255, COLORMAP_TURBO, invalid black
+    valid = ~np.isnan(disp)
+    norm = cv2.normalize(disp, None, 0, 255, cv2.NORM_MINMAX, cv2.CV_8UC1, valid.astype(np.uint8))
+    norm[~valid] = 0
+    want = cv2.applyColorMap(norm, cv2.COLORMAP_TURBO)
+    want[~valid] = 0
+    assert (np.abs(png.astype(int) - want.astype(int)).max(axis=2) <= 12).all()  # at most one grey level apart
+    assert (png == want).all(axis=2).mean() > 0.95
+    i16 = rng.integers(-50, 300, size=(30, 44)).astype(np.int16)
+    i16[0, :5] = -32768
+    raw.write_bytes(i16.tobytes())
+    assert subprocess.run([IOCHK, "write", "30", "44", "3", str(raw), str(tmp_path / "o2")]).returncode == 0
+    assert np.array_equal(cv2.imread(str(tmp_path / "o2.tiff"), cv2.IMREAD_UNCHANGED), i16)
+
+
+def test_q_matrix_yaml_and_xml(tmp_path):
+    q = np.arange(16, dtype=np.float64).reshape(4, 4) * 1.5 - 3
+    for ext in ("yaml", "xml"):
+        path = str(tmp_path / f"q.{ext}")
+        fs = cv2.FileStorage(path, cv2.FILE_STORAGE_WRITE)
+        fs.write("Q", q)
+        fs.release()
+        res = subprocess.run([IOCHK, "q", path], capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+        assert np.allclose(np.array(res.stdout.split(), dtype=np.float64), q.ravel())
+
+
 def _write_stacks(folder, left, right, paired, ext):
     os.makedirs(folder, exist_ok=True)
     if paired:
