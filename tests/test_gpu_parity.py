@@ -302,6 +302,25 @@ def test_double_precision_against_reference_cuda_build(handle, oracles):
         assert np.max(np.abs(ref_c[ev] - got_c[ev])) <= 1e-12
 
 
+def test_negative_threshold_evaluates_but_rejects_nothing(handle, oracles):
+    """BICOS::Config{.nxcorr_threshold = -1}: what the reference CLI uses for --corrmap without
+    --threshold (cli.cpp:150-153). The correlation map equals that of any other threshold, and every
+    pixel whose correlation was evaluated keeps its raw disparity."""
+    left, right, _ = synth.make_stacks(33, 256, 320, np.uint8, seed=12, row0=90, rows=40)
+    l, r = _cuda(left), _cuda(right)
+    raw, _ = handle.match(l, r, Config(nxcorr_threshold=None, consistency=True, max_lr_diff=1))
+    d0, c0 = handle.match(l, r, Config(nxcorr_threshold=0.9, consistency=True, max_lr_diff=1, min_variance=2.0))
+    dm, cm = handle.match(l, r, Config(nxcorr_threshold=-1.0, consistency=True, max_lr_diff=1, min_variance=2.0))
+    want_c = oracles.port.match(left, right, nxcorr_threshold=0.0, consistency=True, max_lr_diff=1, min_variance=2.0)[1]
+    assert _same(c0.cpu().numpy(), want_c) and _same(cm.cpu().numpy(), want_c)
+    raw, dm, cm = raw.cpu().numpy(), dm.cpu().numpy(), cm.cpu().numpy()
+    evaluated = ~np.isnan(cm)
+    assert evaluated.mean() > 0.5 and (cm[evaluated] < 0.9).any()  # some matches a threshold of 0.9 rejects
+    assert np.array_equal(dm[evaluated], raw[evaluated].astype(np.float32))
+    assert (dm[~evaluated] == -32768).all()
+    assert (d0.cpu().numpy()[evaluated & (cm < 0.9)] == -32768).all()
+
+
 def test_match_host_and_rows(handle, oracles):
     """Host-buffer entry point and the row-sharded entry point give the same answer."""
     import torch
