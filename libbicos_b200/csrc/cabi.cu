@@ -764,8 +764,24 @@ int bicos_b200_match_host_begin(bicos_b200_handle h, const void* const* host_pla
             CU(cudaEventCreateWithFlags(&h->ev_done[b], cudaEventDisableTiming));
         }
     }
-    int bands = rows / 192; // measured best at 2048 columns (96 .. 768 rows per band tried)
-    bands = bands < 1 ? 1 : bands > MAX_BANDS ? MAX_BANDS : bands;
+    // Band boundaries: about 192 rows each (measured best at 2048 columns, 96 .. 768 tried), with
+    // a short first band so that the first kernels start early and a short last band so that
+    // little work trails the last upload.
+    int cut[MAX_BANDS + 1];
+    int bands = 0;
+    {
+        int inner = rows / 192;
+        inner = inner < 1 ? 1 : inner > MAX_BANDS - 2 ? MAX_BANDS - 2 : inner;
+        const int edge = rows >= 4 * 192 ? 64 : 0; // only worth it when there are several bands anyway
+        cut[bands++] = 0;
+        if (edge)
+            cut[bands++] = edge;
+        for (int b = 1; b < inner; ++b)
+            cut[bands++] = edge + (int)((long long)(rows - 2 * edge) * b / inner);
+        if (edge)
+            cut[bands++] = rows - edge;
+        cut[bands] = rows;
+    }
 
     const size_t eb = depth_bytes(depth);
     const size_t row_bytes = (size_t)cols * eb;
@@ -774,7 +790,9 @@ int bicos_b200_match_host_begin(bicos_b200_handle h, const void* const* host_pla
     const size_t disp_eb = has_thr(cfg) ? 4 : 2;
     const size_t corr_eb = cfg->precision != 0 ? 8 : 4;
     const bool want_corr = host_corrmap && has_thr(cfg);
-    const int band_rows_max = (rows + bands - 1) / bands + 1;
+    int band_rows_max = 1;
+    for (int b = 0; b < bands; ++b)
+        band_rows_max = cut[b + 1] - cut[b] > band_rows_max ? cut[b + 1] - cut[b] : band_rows_max;
     {
         // reserve everything up front: a reallocation inside the pipeline would stall it
         int K = 0;
@@ -827,7 +845,7 @@ int bicos_b200_match_host_begin(bicos_b200_handle h, const void* const* host_pla
     // far ahead of the device with copy submissions while kernels wait to be launched
     auto enqueue = [&]() -> int {
         for (int b = 0; b < bands; ++b) {
-            const int rb = (int)((long long)rows * b / bands), re = (int)((long long)rows * (b + 1) / bands);
+            const int rb = cut[b], re = cut[b + 1];
             if (stage_inputs) {
                 const int slot = b % PIN_SLOTS;
                 if (b >= PIN_SLOTS)
