@@ -321,6 +321,7 @@ def main():
         "kernel": "search_kernel<4, CONSISTENCY>", "bound": "popc", "achieved": popc_alg / t_se / 1e12,
         "peak": popc_peak / 1e12, "unit": "Tpopc32/s", "frac": popc_alg / t_se / popc_peak,
         "pipe_frac": popc_issued / t_se / popc_peak, "traffic": traffic.get("search"),
+        "hbm_frac": (traffic.get("search", 0) / t_se / 1e9 / hbm_peak) if traffic.get("search") else None,
         "peak_source": popc_src, "ms_per_launch": t_se * 1e3,
         "note": "frac = algorithmic popc32 (SURVEY 8d: 4 words per 128-bit pair) over the measured POPC issue rate; the "
                 "kernel issues 3 POPC per pair after carry-save compression, so frac exceeds 1 while pipe_frac (issued "
