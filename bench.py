@@ -196,7 +196,7 @@ def main():
         import oracle  # baselines are timed beside the product, never inside it
         from tools import bench_configs
 
-        bench_configs.run_table(["C1", "C2", "metric", "C3", "C4", "C5"], 10,
+        bench_configs.run_table(["C1", "C2", "metric", "C3", "C3n20", "C4", "C5"], 10,
                                 oracle.refcuda if oracle.refcuda.available() else None)
         return
 

@@ -54,7 +54,8 @@ using Image = cv::cuda::GpuMat;
 // Which temporal descriptor is built per pixel from the n images of a stack:
 //   LIMITED  neighbour, mean and neighbouring pair-sum comparisons: 4n-6 bits, n <= 65
 //   FULL     additionally all pair-sum against pair-sum comparisons: n^2-2n+3 bits, n <= 16
-// (descriptors are held in 32 / 64 / 128 / 256 bits; wider stacks are rejected)
+// (descriptors are held in 32 / 64 / 128 / 256 bits; wider stacks are rejected unless
+// Config::wide_descriptors allows 384 / 512 bits, FULL n <= 23)
 enum class TransformMode { LIMITED, FULL };
 
 // Arithmetic of the normalised cross correlation; the correlation map is float32 or float64
@@ -91,6 +92,9 @@ struct Config {
     TransformMode mode = TransformMode::LIMITED;
     Precision precision = Precision::SINGLE;
     SearchVariant variant = Variant::NoDuplicates {};
+    // Extension beyond the reference (leave false for its behaviour): descriptors of 384 and 512
+    // bits, i.e. FULL stacks of 17..23 images, which the reference rejects as "too large".
+    bool wide_descriptors = false;
 };
 
 // Thrown for invalid input (fewer than two images, unsupported depth, mismatching stacks) and

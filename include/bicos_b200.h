@@ -63,7 +63,15 @@ typedef struct {
      * though it is negative (BICOS::Config{.nxcorr_threshold = -1.0f}: "evaluate the NXC, reject
      * nothing", what the reference CLI uses for --corrmap without --threshold, cli.cpp:150-153) */
     int negative_threshold_is_set;
+    /* extension: nonzero = descriptors of 384 and 512 bits (12 / 16 words) are allowed, i.e. FULL
+     * stacks of 17..23 images, which the reference rejects ("input stacks too large",
+     * src/impl/cpu.cpp:154-155, src/impl/cuda.cu:519-520). 0 = the reference's limit of 256 bits. */
+    int wide_descriptors;
 } bicos_b200_config;
+
+/* `mode` arguments outside a config (bicos_b200_descriptor_words, bicos_b200_transform): bit 0 is
+ * the TransformMode, OR-ing this in allows wide descriptors as bicos_b200_config::wide_descriptors does */
+#define BICOS_B200_MODE_WIDE 2
 
 typedef struct bicos_b200_handle_s* bicos_b200_handle;
 
@@ -79,7 +87,8 @@ int bicos_b200_create(bicos_b200_handle* out, int device);
 int bicos_b200_destroy(bicos_b200_handle h);
 
 /* Words (uint32) per descriptor the reference's dispatch picks for n images
- * (src/impl/cpu.cpp:122-156): 1/2/4/8, or BICOS_B200_ERR_INVALID above 256 bits. */
+ * (src/impl/cpu.cpp:122-156): 1/2/4/8, or BICOS_B200_ERR_INVALID above 256 bits (with
+ * BICOS_B200_MODE_WIDE in `mode`: 12 / 16 up to 512 bits). */
 int bicos_b200_descriptor_words(int n, int mode);
 
 /* Result type codes for a configuration: disparity BICOS_B200_16S (no threshold) or

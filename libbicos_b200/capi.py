@@ -47,6 +47,7 @@ class CConfig(ctypes.Structure):
         ("max_lr_diff", ctypes.c_int),
         ("no_dupes", ctypes.c_int),
         ("negative_threshold_is_set", ctypes.c_int),  # extension, see include/bicos_b200.h
+        ("wide_descriptors", ctypes.c_int),  # extension: 384 / 512-bit descriptors (FULL, 17..23 images)
     ]
 
 
@@ -62,6 +63,7 @@ class Config:
     consistency: bool = False  # Variant::Consistency instead of Variant::NoDuplicates
     max_lr_diff: int = 1
     no_dupes: bool = False
+    wide_descriptors: bool = False  # extension beyond the reference: FULL stacks of 17..23 images
 
     def to_c(self) -> CConfig:
         def opt(v):
@@ -70,7 +72,8 @@ class Config:
         negative = self.nxcorr_threshold is not None and not self.nxcorr_threshold >= 0
         return CConfig(opt(self.nxcorr_threshold), opt(self.subpixel_step), opt(self.min_variance),
                        int(self.mode_full), int(self.double), int(self.consistency),
-                       int(self.max_lr_diff), int(self.no_dupes), int(negative))
+                       int(self.max_lr_diff), int(self.no_dupes), int(negative),
+                       int(self.wide_descriptors))
 
     @property
     def flags(self) -> int:
@@ -127,8 +130,12 @@ def _check(rc: int) -> int:
     return rc
 
 
-def descriptor_words(n: int, mode_full: bool = False) -> int:
-    return _check(lib().bicos_b200_descriptor_words(n, int(mode_full)))
+MODE_WIDE = 2  # BICOS_B200_MODE_WIDE
+
+
+def descriptor_words(n: int, mode_full: bool = False, wide: bool = False) -> int:
+    """Words per descriptor: 1/2/4/8 as the reference dispatches them; `wide` (extension) adds 12 / 16."""
+    return _check(lib().bicos_b200_descriptor_words(n, int(mode_full) | (MODE_WIDE if wide else 0)))
 
 
 def _ptr_array(ptrs: Sequence[int]):
@@ -188,15 +195,16 @@ class Handle:
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     # ---- stages -------------------------------------------------------------------------
-    def transform(self, stack, mode_full: bool = False):
+    def transform(self, stack, mode_full: bool = False, wide: bool = False):
         """Descriptor transform of one stack -> int32 tensor [rows, cols, K] (a view of pitched rows)."""
         import torch
 
         planes, n, rows, cols, pitch, depth = self._stack_info(stack)
-        k = descriptor_words(n, mode_full)
+        k = descriptor_words(n, mode_full, wide)
         pitch_words = (cols * k + 3) // 4 * 4
         desc = torch.empty((rows, pitch_words), dtype=torch.int32, device=stack.device)
-        _check(lib().bicos_b200_transform(self._h, planes, n, rows, cols, pitch, depth, int(mode_full),
+        _check(lib().bicos_b200_transform(self._h, planes, n, rows, cols, pitch, depth,
+                                          int(mode_full) | (MODE_WIDE if wide else 0),
                                           desc.data_ptr(), pitch_words, self._stream()))
         return desc, k
 

@@ -216,7 +216,9 @@ int descriptor_bits(int n, int mode) {
     return mode ? n * n - 2 * n + 3 : 4 * n - 7;
 }
 
-int words_for_bits(int bits) {
+// src/impl/cpu.cpp:131-156: 32 / 64 / 128 / 256 bits, more is rejected. `wide` (extension, off by
+// default): 384 and 512 bits as well, i.e. FULL stacks of 17..23 images.
+int words_for_bits(int bits, bool wide) {
     if (bits <= 32)
         return 1;
     if (bits <= 64)
@@ -225,7 +227,19 @@ int words_for_bits(int bits) {
         return 4;
     if (bits <= 256)
         return 8;
+    if (wide && bits <= 384)
+        return 12;
+    if (wide && bits <= 512)
+        return 16;
     return -1;
+}
+
+// `mode` arguments of the stage entry points: bit 0 = FULL, bit 1 = BICOS_B200_MODE_WIDE
+bool mode_is_full(int mode) {
+    return (mode & 1) != 0;
+}
+bool cfg_is_wide(const bicos_b200_config* cfg) {
+    return cfg->wide_descriptors != 0 || (cfg->mode & BICOS_B200_MODE_WIDE) != 0;
 }
 
 // is the NXC stage on? (see bicos_b200_config::negative_threshold_is_set)
@@ -276,8 +290,8 @@ int validate_common(int n, int rows, int cols, int depth, const bicos_b200_confi
         return fail(BICOS_B200_ERR_INVALID, "need at least two images"); // cpu.cpp:110-111
     if (depth != BICOS_B200_8U && depth != BICOS_B200_16U)
         return fail(BICOS_B200_ERR_INVALID, "bad input depths, only CV_8UC1 and CV_16UC1 are supported"); // cpu.cpp:113-114
-    const int bits = descriptor_bits(n, cfg->mode != 0);
-    const int K = words_for_bits(bits);
+    const int bits = descriptor_bits(n, mode_is_full(cfg->mode));
+    const int K = words_for_bits(bits, cfg_is_wide(cfg));
     if (K < 0 || n > MAX_IMAGES)
         return fail(BICOS_B200_ERR_INVALID, "input stacks too large, would require %d bits", bits); // cpu.cpp:154-155
     if (rows <= 0 || cols <= 0)
@@ -492,8 +506,8 @@ int do_match(
     const int is_u16 = depth == BICOS_B200_16U;
     if (int rc = prof_mark(h, stream))
         return rc;
-    CU(launch_transform(t0, n, nrows, cols, pitch_bytes, is_u16, cfg->mode != 0, K, d0, dpw, stream));
-    CU(launch_transform(t1, n, nrows, cols, pitch_bytes, is_u16, cfg->mode != 0, K, d1, dpw, stream));
+    CU(launch_transform(t0, n, nrows, cols, pitch_bytes, is_u16, mode_is_full(cfg->mode), K, d0, dpw, stream));
+    CU(launch_transform(t1, n, nrows, cols, pitch_bytes, is_u16, mode_is_full(cfg->mode), K, d1, dpw, stream));
     h->launches += 2;
     if (int rc = prof_mark(h, stream))
         return rc;
@@ -587,8 +601,8 @@ int bicos_b200_destroy(bicos_b200_handle h) {
 int bicos_b200_descriptor_words(int n, int mode) {
     if (n < 2)
         return fail(BICOS_B200_ERR_INVALID, "need at least two images");
-    const int bits = descriptor_bits(n, mode != 0);
-    const int K = words_for_bits(bits);
+    const int bits = descriptor_bits(n, mode_is_full(mode));
+    const int K = words_for_bits(bits, (mode & BICOS_B200_MODE_WIDE) != 0);
     if (K < 0 || n > MAX_IMAGES)
         return fail(BICOS_B200_ERR_INVALID, "input stacks too large, would require %d bits", bits);
     return K;
@@ -621,7 +635,7 @@ int bicos_b200_transform(bicos_b200_handle h, const void* const* planes, int n, 
     PlaneTable t;
     if (int rc = fill_table(t, planes, n, 0))
         return rc;
-    CU(launch_transform(t, n, rows, cols, pitch_bytes, depth == BICOS_B200_16U, mode != 0, K, desc, desc_pitch_words, static_cast<cudaStream_t>(stream)));
+    CU(launch_transform(t, n, rows, cols, pitch_bytes, depth == BICOS_B200_16U, mode_is_full(mode), K, desc, desc_pitch_words, static_cast<cudaStream_t>(stream)));
     h->launches += 1;
     return 0;
 }
@@ -631,8 +645,8 @@ int bicos_b200_search(bicos_b200_handle h, const uint32_t* desc0, const uint32_t
                       uint32_t* fwd_last, uint32_t* rev_first, uint32_t* rev_last, void* stream) {
     if (!h || !desc0 || !desc1 || !fwd_first)
         return fail(BICOS_B200_ERR_INVALID, "null argument");
-    if (K != 1 && K != 2 && K != 4 && K != 8)
-        return fail(BICOS_B200_ERR_INVALID, "K must be 1, 2, 4 or 8");
+    if (K != 1 && K != 2 && K != 4 && K != 8 && K != 12 && K != 16)
+        return fail(BICOS_B200_ERR_INVALID, "K must be 1, 2, 4 or 8 (12 or 16 for wide descriptors)");
     if (flags < 0 || flags > 3)
         return fail(BICOS_B200_ERR_INVALID, "bad flags");
     if (rows <= 0 || cols <= 0 || cols > 32767)

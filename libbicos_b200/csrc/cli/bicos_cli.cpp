@@ -4,7 +4,7 @@
 // include/BICOS/match.hpp.
 //
 //   bicos-cli folder0 [folder1] [-t thr] [-v var] [-s step] [-o out.png] [-n N] [-q Q.yaml]
-//             [--allow-negative-z] [-m lr-maxdiff] [--double] [--limited] [--corrmap] [--no-dupes]
+//             [--allow-negative-z] [-m lr-maxdiff] [--double] [--limited] [--corrmap] [--no-dupes] [--wide-descriptors]
 //
 // Differences, on purpose: --allow-negative-z is honoured (the reference reads a non-existent
 // "allow-behind" option, cli.cpp:231); integer-mode disparities with a threshold are float32
@@ -60,6 +60,7 @@ const Option OPTIONS[] = {
     { "limited", 0, false, "Limit transformation mode. Allows for more images to be used." },
     { "corrmap", 0, false, "Output map of normalized cross correlation values." },
     { "no-dupes", 0, false, "Default BICOS variant when --lr-maxdiff is not specified. Can be set together with --lr-maxdiff to activate both." },
+    { "wide-descriptors", 0, false, "Extension: accept 17..23 images without --limited (384 / 512-bit descriptors; the reference stops at 16)." },
     { "help", 'h', false, "Display this message." },
 };
 
@@ -339,6 +340,8 @@ int run(int argc, char const* const* argv) {
         c.min_variance = minvar;
     if (args.has("double"))
         c.precision = Precision::DOUBLE;
+    if (args.has("wide-descriptors"))
+        c.wide_descriptors = true;
     if (args.has("lr-maxdiff"))
         c.variant = Variant::Consistency { (int)to_uint(args, "lr-maxdiff"), args.has("no-dupes") };
 

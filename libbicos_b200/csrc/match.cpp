@@ -60,6 +60,7 @@ bicos_b200_config to_c_config(const Config& cfg) {
     c.min_variance = cfg.min_variance.value_or(-1.f);
     c.mode = cfg.mode == TransformMode::FULL ? 1 : 0;
     c.precision = cfg.precision == Precision::DOUBLE ? 1 : 0;
+    c.wide_descriptors = cfg.wide_descriptors ? 1 : 0;
     if (std::holds_alternative<Variant::Consistency>(cfg.variant)) {
         const auto& v = std::get<Variant::Consistency>(cfg.variant);
         c.variant_type = 1;

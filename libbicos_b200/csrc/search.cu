@@ -82,9 +82,35 @@ __device__ __forceinline__ Desc<K> load_desc(const uint32_t* p) {
     return d;
 }
 
-// popcount(l ^ r) over K words (reference ham(), bicos.hpp:29-48)
+struct Csa {
+    uint32_t s, c; // ones and twos of a + b + c, bit position by bit position
+};
+
+__device__ __forceinline__ Csa csa(uint32_t a, uint32_t b, uint32_t c) {
+    return { xor3(a, b, c), maj3(a, b, c) };
+}
+
+// a * m + c as one IMAD with m a run-time 1 or 2 (SearchArgs::one / two): ptxas would otherwise emit
+// part of the popcount sums as IADD3 / LEA, i.e. on the ALU pipe the LOP3s already fill, while the FMA
+// pipe idles.
+__device__ __forceinline__ uint32_t mad(uint32_t a, uint32_t m, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(m), "r"(c));
+    return d;
+}
+
+struct Weights {
+    uint32_t one, two, shl16; // 1, 2, 65536
+};
+
+// popcount(l ^ r) over K words (reference ham(), bicos.hpp:29-48). Every carry-save adder trades one
+// POPC (8 issue cycles of the 16-lane XU pipe per warp) for two LOP3 (2 x 2 cycles of the ALU pipe).
+// From 256 bits on the ALU pipe is the busier one; `light` pairs skip the last adder and spend one more
+// POPC instead. Measured (tools/search_tune, MIX = light pairs per thread): no mix beats MIX = 0 at
+// 256 bits (0.857 / 0.831 / 0.841 T pairs/s for MIX 0 / 1 / 2) and the differences at 384 / 512 bits
+// are below 1 %, so the full trees are the default and `light` stays a tuning knob.
 template<int K>
-__device__ __forceinline__ uint32_t hamming(const Desc<K>& l, const Desc<K>& r) {
+__device__ __forceinline__ uint32_t hamming(const Desc<K>& l, const Desc<K>& r, bool light, const Weights w) {
     uint32_t x[K];
 #pragma unroll
     for (int k = 0; k < K; ++k)
@@ -95,19 +121,41 @@ __device__ __forceinline__ uint32_t hamming(const Desc<K>& l, const Desc<K>& r) 
         return __popc(x[0]) + __popc(x[1]);
     } else if constexpr (K == 4) {
         // full adder over three words: ones in s, twos in c -> 3 POPC instead of 4
-        const uint32_t s = xor3(x[0], x[1], x[2]);
-        const uint32_t c = maj3(x[0], x[1], x[2]);
-        return __popc(s) + __popc(x[3]) + 2 * __popc(c);
+        const Csa a = csa(x[0], x[1], x[2]);
+        return __popc(a.s) + __popc(x[3]) + 2 * __popc(a.c);
+    } else if constexpr (K == 8) {
+        const Csa a = csa(x[0], x[1], x[2]), b = csa(x[3], x[4], x[5]), c = csa(a.s, b.s, x[6]);
+        const uint32_t ones = mad(__popc(c.s), w.one, __popc(x[7]));
+        if (light) // 3 adders, 5 POPC
+            return mad(mad(mad(__popc(a.c), w.one, __popc(b.c)), w.one, __popc(c.c)), w.two, ones);
+        const Csa t = csa(a.c, b.c, c.c); // 4 adders, 4 POPC: ones c.s x7, twos t.s, fours t.c
+        return mad(mad(__popc(t.c), w.two, __popc(t.s)), w.two, ones);
+    } else if constexpr (K == 12) {
+        const Csa a = csa(x[0], x[1], x[2]), b = csa(x[3], x[4], x[5]), c = csa(x[6], x[7], x[8]), d = csa(x[9], x[10], x[11]);
+        const Csa e = csa(a.s, b.s, c.s);
+        const uint32_t ones = mad(__popc(e.s), w.one, __popc(d.s));
+        const uint32_t de = mad(__popc(d.c), w.one, __popc(e.c));
+        if (light) // 5 adders, 7 POPC
+            return mad(mad(mad(mad(__popc(a.c), w.one, __popc(b.c)), w.one, __popc(c.c)), w.one, de), w.two, ones);
+        const Csa t = csa(a.c, b.c, c.c); // 6 adders, 6 POPC: twos t.s d.c e.c, fours t.c
+        return mad(mad(mad(__popc(t.c), w.two, __popc(t.s)), w.one, de), w.two, ones);
     } else {
-        // carry-save tree over eight words -> 4 POPC instead of 8
-        const uint32_t s1 = xor3(x[0], x[1], x[2]), c1 = maj3(x[0], x[1], x[2]);
-        const uint32_t s2 = xor3(x[3], x[4], x[5]), c2 = maj3(x[3], x[4], x[5]);
-        const uint32_t s3 = xor3(s1, s2, x[6]), c3 = maj3(s1, s2, x[6]);
-        // ones: s3, x7; twos: c1 c2 c3 -> one more full adder gives twos t and fours f
-        const uint32_t t = xor3(c1, c2, c3), f = maj3(c1, c2, c3);
-        return __popc(s3) + __popc(x[7]) + 2 * __popc(t) + 4 * __popc(f);
+        static_assert(K == 16, "descriptor widths: 1, 2, 4, 8, 12 or 16 words");
+        const Csa a = csa(x[0], x[1], x[2]), b = csa(x[3], x[4], x[5]), c = csa(x[6], x[7], x[8]), d = csa(x[9], x[10], x[11]),
+                  e = csa(x[12], x[13], x[14]);
+        const Csa f = csa(a.s, b.s, c.s), g = csa(d.s, e.s, x[15]);
+        const uint32_t ones = mad(__popc(f.s), w.one, __popc(g.s));
+        const uint32_t defg = mad(mad(mad(__popc(d.c), w.one, __popc(e.c)), w.one, __popc(f.c)), w.one, __popc(g.c));
+        if (light) // 7 adders, 9 POPC
+            return mad(mad(mad(mad(__popc(a.c), w.one, __popc(b.c)), w.one, __popc(c.c)), w.one, defg), w.two, ones);
+        const Csa t = csa(a.c, b.c, c.c); // 8 adders, 8 POPC: twos t.s d.c e.c f.c g.c, fours t.c
+        return mad(mad(mad(__popc(t.c), w.two, __popc(t.s)), w.one, defg), w.two, ones);
     }
 }
+
+// how many of a thread's A left pixels use the `light` distance
+template<int K>
+constexpr int DEFAULT_MIX = 0;
 
 struct SearchArgs {
     const uint32_t* desc0;
@@ -119,6 +167,7 @@ struct SearchArgs {
     int steps_per_unit; // cols rounded up to STEP_ALIGN
     long long total_steps; // rows * units_per_row * steps_per_unit
     int splits; // CTAs per unit
+    uint32_t one, two, shl16; // 1, 2 and 65536 as run-time values, see mad()
     uint32_t* fwd_first;
     uint32_t* fwd_last;
     uint32_t* rev_first;
@@ -126,7 +175,7 @@ struct SearchArgs {
 };
 
 // All steps [s, s_end) of the (row, unit, column) space, unit by unit.
-template<int K, int FLAGS, int A, int NT, int UNROLL>
+template<int K, int FLAGS, int A, int NT, int UNROLL, int MIX>
 __device__ __forceinline__ void search_range(const SearchArgs& p, long long s, const long long s_end, uint4* smem_raw) {
     constexpr bool NODUPES = (FLAGS & FLAG_NODUPES) != 0;
     constexpr bool REVERSE = (FLAGS & FLAG_CONSISTENCY) != 0;
@@ -139,6 +188,7 @@ __device__ __forceinline__ void search_range(const SearchArgs& p, long long s, c
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int cols = p.cols;
+    const Weights wts = { p.one, p.two, p.shl16 };
 
     while (s < s_end) {
         const long long ru = s / p.steps_per_unit;
@@ -201,18 +251,33 @@ __device__ __forceinline__ void search_range(const SearchArgs& p, long long s, c
                 for (int u = 0; u < m; ++u) {
                     const Desc<K> r = load_desc<K>(s_right + (size_t)(jj0 + u) * K); // warp-uniform: broadcast
                     const uint32_t j = (uint32_t)(j0 + jj0 + u);
-                    const uint32_t jrev = 65535u - j;
+                    uint32_t jrev = 65535u - j;
+                    if constexpr (NODUPES)
+                        asm("" : "+r"(jrev)); // one subtraction per column, not re-associated into every pair's add
                     uint32_t ck = KEY_NONE, ckl = KEY_NONE;
 #pragma unroll
                     for (int a = 0; a < A; ++a) {
-                        const uint32_t cost16 = hamming<K>(l[a], r) << 16;
-                        mf[a] = min(mf[a], cost16 + j);
-                        if constexpr (NODUPES)
-                            ml[a] = min(ml[a], cost16 + jrev);
-                        if constexpr (REVERSE) {
-                            ck = min(ck, cost16 + icol[a]);
+                        const uint32_t h = hamming<K>(l[a], r, a >= A - MIX, wts);
+                        if constexpr (K >= 8) {
+                            // ALU-pipe bound widths: keys built by IMAD (run-time 65536), only the minima on the ALU pipe
+                            mf[a] = min(mf[a], mad(h, wts.shl16, j));
                             if constexpr (NODUPES)
-                                ckl = min(ckl, cost16 + icol_rev[a]);
+                                ml[a] = min(ml[a], mad(h, wts.shl16, jrev));
+                            if constexpr (REVERSE) {
+                                ck = min(ck, mad(h, wts.shl16, icol[a]));
+                                if constexpr (NODUPES)
+                                    ckl = min(ckl, mad(h, wts.shl16, icol_rev[a]));
+                            }
+                        } else {
+                            const uint32_t cost16 = h << 16;
+                            mf[a] = min(mf[a], cost16 + j);
+                            if constexpr (NODUPES)
+                                ml[a] = min(ml[a], cost16 + jrev);
+                            if constexpr (REVERSE) {
+                                ck = min(ck, cost16 + icol[a]);
+                                if constexpr (NODUPES)
+                                    ckl = min(ckl, cost16 + icol_rev[a]);
+                            }
                         }
                     }
                     if constexpr (REVERSE) {
@@ -268,7 +333,7 @@ __device__ __forceinline__ void search_range(const SearchArgs& p, long long s, c
 }
 
 // `splits` CTAs per unit, each an equal slice of the unit's columns.
-template<int K, int FLAGS, int A, int NT, int UNROLL>
+template<int K, int FLAGS, int A, int NT, int UNROLL, int MIX>
 __global__ void __launch_bounds__(NT) search_kernel(const SearchArgs p) {
     extern __shared__ uint4 smem_raw[];
     const long long ru = blockIdx.x / p.splits;
@@ -278,7 +343,7 @@ __global__ void __launch_bounds__(NT) search_kernel(const SearchArgs p) {
     const long long s = base + (long long)part * span;
     const long long s_end = min(base + p.steps_per_unit, s + span);
     if (s < s_end)
-        search_range<K, FLAGS, A, NT, UNROLL>(p, s, s_end, smem_raw);
+        search_range<K, FLAGS, A, NT, UNROLL, MIX>(p, s, s_end, smem_raw);
 }
 
 int chunk_for(int K, int cols) {
@@ -316,7 +381,7 @@ int sm_count() {
 }
 
 // splits <= 0: chosen here from the grid size
-template<int K, int FLAGS, int A, int NT = THREADS, int UNROLL = 2>
+template<int K, int FLAGS, int A, int NT = THREADS, int UNROLL = 2, int MIX = DEFAULT_MIX<K>>
 cudaError_t launch_one(
     const uint32_t* desc0,
     const uint32_t* desc1,
@@ -351,12 +416,15 @@ cudaError_t launch_one(
         splits = splits > MAX_SPLITS ? MAX_SPLITS : splits < 1 ? 1 : splits;
     }
     p.splits = splits;
+    p.one = 1u;
+    p.two = 2u;
+    p.shl16 = 65536u;
     p.fwd_first = fwd_first;
     p.fwd_last = fwd_last;
     p.rev_first = rev_first;
     p.rev_last = rev_last;
     const int smem = search_smem_bytes(K, cols, FLAGS);
-    auto kernel = search_kernel<K, FLAGS, A, NT, UNROLL>;
+    auto kernel = search_kernel<K, FLAGS, A, NT, UNROLL, MIX>;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess)
         return err;
@@ -452,6 +520,10 @@ cudaError_t launch_search(
             return launch_k<4>(desc0, desc1, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, stream);
         case 8:
             return launch_k<8>(desc0, desc1, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, stream);
+        case 12: // wide-descriptor extension (bicos_b200_config::wide_descriptors): FULL stacks of 17..20 images
+            return launch_k<12>(desc0, desc1, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, stream);
+        case 16: // FULL stacks of 21..23 images
+            return launch_k<16>(desc0, desc1, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, stream);
     }
     return cudaErrorInvalidValue;
 }

@@ -453,7 +453,8 @@ __global__ void __launch_bounds__(THREADS) transform_limited_u8x4_kernel(
 
 constexpr int full_words(int n) {
     const int bits = n * n - 2 * n + 3;
-    return bits <= 32 ? 1 : bits <= 64 ? 2 : bits <= 128 ? 4 : 8;
+    // 12 and 16 words: the wide-descriptor extension (17..23 images), beyond the reference's 256 bits
+    return bits <= 32 ? 1 : bits <= 64 ? 2 : bits <= 128 ? 4 : bits <= 256 ? 8 : bits <= 384 ? 12 : 16;
 }
 
 template<typename TIn, int N>
@@ -510,6 +511,13 @@ cudaError_t launch_full(
         FULL_CASE(14)
         FULL_CASE(15)
         FULL_CASE(16)
+        FULL_CASE(17)
+        FULL_CASE(18)
+        FULL_CASE(19)
+        FULL_CASE(20)
+        FULL_CASE(21)
+        FULL_CASE(22)
+        FULL_CASE(23)
     }
 #undef FULL_CASE
     return cudaErrorInvalidValue;

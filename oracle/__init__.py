@@ -56,10 +56,18 @@ def _opt(v) -> float:
     return -1.0 if v is None else float(v)
 
 
-def words_per_descriptor(n: int, full: bool) -> int:
-    """Descriptor width choice of the reference driver (src/impl/cpu.cpp:122-156)."""
+MODE_WIDE = 2  # bit 1 of the `mode` ints: allow the 384 / 512-bit extension (FULL, 17..23 images)
+
+
+def _mode(mode_full, wide) -> int:
+    return int(bool(mode_full)) | (MODE_WIDE if wide else 0)
+
+
+def words_per_descriptor(n: int, full: bool, wide: bool = False) -> int:
+    """Descriptor width choice of the reference driver (src/impl/cpu.cpp:122-156); `wide` adds the
+    12- and 16-word descriptors of this repository's extension."""
     bits = n * n - 2 * n + 3 if full else 4 * n - 7
-    for k, cap in ((1, 32), (2, 64), (4, 128), (8, 256)):
+    for k, cap in ((1, 32), (2, 64), (4, 128), (8, 256)) + (((12, 384), (16, 512)) if wide else ()):
         if bits <= cap:
             return k
     raise ValueError(f"input stacks too large, would require {bits} bits")
@@ -105,10 +113,19 @@ class _Lib:
 
     # -- full path -------------------------------------------------------------------------
     def match(self, stack0, stack1, nxcorr_threshold=0.5, subpixel_step=None, min_variance=None,
-              mode_full=False, consistency=False, max_lr_diff=1, no_dupes=False, double=False):
-        """BICOS::match on planar [n, H, W] stacks. Returns (disparity, corrmap or None)."""
+              mode_full=False, consistency=False, max_lr_diff=1, no_dupes=False, double=False, wide_descriptors=False):
+        """BICOS::match on planar [n, H, W] stacks. Returns (disparity, corrmap or None).
+
+        ``wide_descriptors`` (extension, same name as in BICOS::Config): descriptors of 384 / 512 bits. The port handles them in its own driver;
+        for the reference build, whose driver throws above 256 bits (src/impl/cpu.cpp:153-155), the
+        path is composed here from the reference's own stage templates instantiated with
+        std::bitset<384> / <512> (descriptor_transform -> bicos -> agree, the sequence of
+        match_impl, src/impl/cpu.cpp:35-98)."""
         s0, s1 = _c(stack0), _c(stack1)
         n, rows, cols = s0.shape
+        if wide_descriptors and self.prefix == "ref_" and words_per_descriptor(n, mode_full, True) > 8:
+            return self._match_by_stages(s0, s1, nxcorr_threshold, subpixel_step, min_variance, mode_full,
+                                         consistency, max_lr_diff, no_dupes)
         disp_buf = np.empty((rows, cols), dtype=np.float32)
         disp_type = ctypes.c_int(-1)
         if double:
@@ -122,7 +139,7 @@ class _Lib:
         rc = fn(_p(s0), _p(s1), ctypes.c_int(n), ctypes.c_int(rows), ctypes.c_int(cols),
                 ctypes.c_int(_depth(s0)), ctypes.c_float(_opt(nxcorr_threshold)),
                 ctypes.c_float(_opt(subpixel_step)), ctypes.c_float(_opt(min_variance)),
-                ctypes.c_int(int(mode_full)), ctypes.c_int(int(consistency)),
+                ctypes.c_int(_mode(mode_full, wide_descriptors)), ctypes.c_int(int(consistency)),
                 ctypes.c_int(int(max_lr_diff)), ctypes.c_int(int(no_dupes)),
                 _p(disp_buf), ctypes.byref(disp_type), _p(corr))
         self._check(rc)
@@ -132,15 +149,29 @@ class _Lib:
             disp = disp_buf
         return disp, (corr if nxcorr_threshold is not None else None)
 
+    def _match_by_stages(self, s0, s1, nxcorr_threshold, subpixel_step, min_variance, mode_full,
+                         consistency, max_lr_diff, no_dupes):
+        d0 = self.descriptors(s0, mode_full, wide=True)
+        d1 = self.descriptors(s1, mode_full, wide=True)
+        flags = (FLAG_CONSISTENCY | (FLAG_NODUPES if no_dupes else 0)) if consistency else FLAG_NODUPES  # cpu.cpp:68-75
+        raw = self.bicos(d0, d1, flags, max_lr_diff if consistency else -1)
+        if nxcorr_threshold is None:
+            return raw, None
+        disp, corr = self.agree(raw, s0, s1, nxcorr_threshold, subpixel_step, min_variance)
+        if subpixel_step is None:
+            disp = disp.astype(np.float32)  # cpu.cpp:88-94: convertTo keeps -32768 as -32768.0f
+        # cpu.cpp:78-81: the map starts as NaN; agree() of the harness does the same
+        return disp, corr
+
     # -- stages ----------------------------------------------------------------------------
-    def descriptors(self, stack, mode_full=False):
+    def descriptors(self, stack, mode_full=False, wide=False):
         """[H, W, K] uint32 words, bit i of the descriptor = bit i%32 of word i//32."""
         s = _c(stack)
         n, rows, cols = s.shape
-        out = np.zeros((rows, cols, 8), dtype=np.uint32)
+        out = np.zeros((rows, cols, 16), dtype=np.uint32)
         k = self._check(self._fn("descriptors")(
             _p(s), ctypes.c_int(n), ctypes.c_int(rows), ctypes.c_int(cols), ctypes.c_int(_depth(s)),
-            ctypes.c_int(int(mode_full)), _p(out), ctypes.c_int(8)))
+            ctypes.c_int(_mode(mode_full, wide)), _p(out), ctypes.c_int(16)))
         # the C side packs K words per pixel densely
         return out.reshape(-1)[: rows * cols * k].reshape(rows, cols, k).copy()
 

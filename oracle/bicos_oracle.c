@@ -38,7 +38,7 @@
 #define FLAG_CONSISTENCY 2  /* include/impl/common.hpp:47 */
 #define INVALID_I16 ((int16_t)-32768) /* include/common.hpp:34-37: lowest() for integers */
 #define INVALID_COL INT_MIN           /* INVALID_DISP<int> */
-#define MAXW 8
+#define MAXW 16 /* 8 words = the reference's 256 bits; 12 / 16 only with the wide extension */
 
 static _Thread_local char g_error[256];
 static int g_threads = 0;
@@ -123,8 +123,11 @@ static uint16_t* widen(const void* stack, int n, int rows, int cols, int depth) 
     return out;
 }
 
-/* src/impl/cpu.cpp:122-156: required_bits (LIMITED undercounts by one, harmless) -> word count */
-static int words_for(int n, int mode_full, int* bits_out) {
+/* src/impl/cpu.cpp:122-156: required_bits (LIMITED undercounts by one, harmless) -> word count.
+ * `mode`: bit 0 = TransformMode::FULL; bit 1 = the wide-descriptor extension of this repository
+ * (384 / 512 bits, FULL stacks of 17..23 images; the reference throws above 256 bits, :153-155). */
+static int words_for(int n, int mode, int* bits_out) {
+    const int mode_full = mode & 1;
     const int bits = mode_full ? n * n - 2 * n + 3 : 4 * n - 7;
     if (bits_out)
         *bits_out = bits;
@@ -136,6 +139,10 @@ static int words_for(int n, int mode_full, int* bits_out) {
         return 4;
     if (bits <= 256)
         return 8;
+    if ((mode & 2) && bits <= 384)
+        return 12;
+    if ((mode & 2) && bits <= 512)
+        return 16;
     return -1;
 }
 
@@ -229,7 +236,7 @@ static void descriptors_row(int r, void* vctx) {
 
 static void descriptors_of(const uint16_t* st, int n, int rows, int cols, int mode_full, int K,
                            uint32_t* out) {
-    desc_ctx x = { st, n, rows, cols, mode_full, K, out };
+    desc_ctx x = { st, n, rows, cols, mode_full & 1, K, out }; /* bit 1 only widens the dispatch */
     for_rows(rows, descriptors_row, &x);
 }
 
@@ -509,7 +516,7 @@ int orc_descriptors(const void* stack, int n, int rows, int cols, int depth, int
 
 int orc_bicos(const uint32_t* desc0, const uint32_t* desc1, int K, int rows, int cols, int flags,
               int max_lr_diff, int16_t* out) {
-    if (K != 1 && K != 2 && K != 4 && K != 8)
+    if (K != 1 && K != 2 && K != 4 && K != 8 && K != 12 && K != 16)
         return fail("bad K");
     if (flags < 1 || flags > 3)
         return fail("bad flags");

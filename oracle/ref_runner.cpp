@@ -82,20 +82,23 @@ struct Words<uint128_t> {
         return d;
     }
 };
-template<>
-struct Words<std::bitset<256>> {
-    static constexpr int K = 8;
-    static void put(const std::bitset<256>& d, uint32_t* w) {
-        for (int i = 0; i < 8; ++i) {
+// std::bitset<256> is what the reference dispatches to above 128 bits (src/impl/cpu.cpp:146-151);
+// bitset<384> / bitset<512> feed the SAME stage templates for the wide-descriptor extension of this
+// repository (FULL stacks of 17..23 images, which the reference's dispatch rejects at :153-155)
+template<size_t NBITS>
+struct Words<std::bitset<NBITS>> {
+    static constexpr int K = NBITS / 32;
+    static void put(const std::bitset<NBITS>& d, uint32_t* w) {
+        for (int i = 0; i < K; ++i) {
             uint32_t x = 0;
             for (int b = 0; b < 32; ++b)
                 x |= (uint32_t)d[32 * i + b] << b;
             w[i] = x;
         }
     }
-    static std::bitset<256> get(const uint32_t* w) {
-        std::bitset<256> d;
-        for (int i = 0; i < 256; ++i)
+    static std::bitset<NBITS> get(const uint32_t* w) {
+        std::bitset<NBITS> d;
+        for (size_t i = 0; i < NBITS; ++i)
             d[i] = (w[i / 32] >> (i % 32)) & 1u;
         return d;
     }
@@ -246,8 +249,12 @@ int ref_descriptors(
         auto planes = planes_of(stack, n, rows, cols, depth);
         cv::Mat merged;
         cv::merge(planes, merged);
+        // mode_full: bit 0 = TransformMode::FULL, bit 1 = allow the 384 / 512-bit extension
+        const bool wide = (mode_full & 2) != 0;
+        mode_full &= 1;
         const int bits = mode_full ? n * n - 2 * n + 3 : 4 * n - 7;
-        const int K = bits <= 32 ? 1 : bits <= 64 ? 2 : bits <= 128 ? 4 : bits <= 256 ? 8 : -1;
+        const int K = bits <= 32 ? 1 : bits <= 64 ? 2 : bits <= 128 ? 4 : bits <= 256 ? 8
+            : wide && bits <= 384 ? 12 : wide && bits <= 512 ? 16 : -1;
         if (K < 0)
             throw std::invalid_argument("too many bits: " + std::to_string(bits));
         if (K > out_capacity_words_per_px)
@@ -269,6 +276,12 @@ int ref_descriptors(
                 break;
             case 8:
                 DISPATCH(std::bitset<256>);
+                break;
+            case 12:
+                DISPATCH(std::bitset<384>);
+                break;
+            case 16:
+                DISPATCH(std::bitset<512>);
                 break;
         }
 #undef DISPATCH
@@ -304,6 +317,12 @@ int ref_bicos(
                 break;
             case 8:
                 bicos_impl<std::bitset<256>>(desc0, desc1, rows, cols, flags, max_lr_diff, out);
+                break;
+            case 12:
+                bicos_impl<std::bitset<384>>(desc0, desc1, rows, cols, flags, max_lr_diff, out);
+                break;
+            case 16:
+                bicos_impl<std::bitset<512>>(desc0, desc1, rows, cols, flags, max_lr_diff, out);
                 break;
             default:
                 throw std::invalid_argument("bad K");

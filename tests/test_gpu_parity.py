@@ -83,7 +83,7 @@ def _random_desc(rng, rows, cols, k, bits):
     return rng.integers(0, 1 << bits, size=(rows, cols, k), dtype=np.int64).astype(np.uint32)
 
 
-@pytest.mark.parametrize("k", [1, 2, 4, 8])
+@pytest.mark.parametrize("k", [1, 2, 4, 8, 12, 16])
 @pytest.mark.parametrize("flags", [FLAG_NODUPES, FLAG_CONSISTENCY, FLAG_NODUPES | FLAG_CONSISTENCY])
 @pytest.mark.parametrize("cols,bits", [(97, 3), (512, 8), (700, 32), (1300, 5)])
 def test_search_postfilter_bit_exact(handle, oracles, k, flags, cols, bits):
@@ -184,6 +184,45 @@ def test_match_double_parity(handle, oracles, n, dtype, rows, cols, kw):
     assert np.max(np.abs(got_c[ok] - want_c[ok]), initial=0) <= 1e-12
     both = ~invalid_w
     assert np.max(np.abs(got_d[both] - want_d[both]), initial=0) <= 1e-3
+
+
+# ------------------------------------------------- wide-descriptor extension (FULL, 17..23 images) --
+@pytest.mark.parametrize("n,dtype,cols", [(17, np.uint8, 200), (18, np.uint16, 131), (20, np.uint16, 288), (20, np.uint8, 97),
+                                          (21, np.uint8, 160), (22, np.uint16, 66), (23, np.uint16, 200)])
+def test_wide_extension_parity(handle, oracles, n, dtype, cols):
+    """BASELINE.json configs[2] names 2x20 uint16 FULL stacks: 363 bits, which the reference rejects. With
+    Config.wide_descriptors the path runs on 12- / 16-word descriptors; the oracle's wide path is pinned against
+    the reference's stage templates (tests/test_oracle.py)."""
+    import libbicos_b200 as lb
+
+    rows = 24
+    left, right, _ = synth.make_stacks(n, 512, cols, dtype, seed=5 * n + cols, row0=96, rows=rows)
+    k_want = 12 if n <= 20 else 16
+    for stack in (left, right):
+        want = oracles.port.descriptors(stack, True, wide=True)
+        desc, k = handle.transform(_cuda(stack), True, wide=True)
+        assert k == k_want == want.shape[2]
+        assert np.array_equal(_words(desc, k, cols), want)
+    for kw in (dict(nxcorr_threshold=None), dict(nxcorr_threshold=0.9, min_variance=1.0),
+               dict(nxcorr_threshold=None, consistency=True, max_lr_diff=1, no_dupes=True),
+               dict(nxcorr_threshold=0.85, subpixel_step=0.2, consistency=True, max_lr_diff=1)):
+        kw = dict(kw, mode_full=True, wide_descriptors=True)
+        want_d, want_c = oracles.port.match(left, right, **kw)
+        disp, corr = handle.match(_cuda(left), _cuda(right), Config(**kw))
+        assert _same(disp.cpu().numpy(), want_d), kw
+        assert (corr is None and want_c is None) or _same(corr.cpu().numpy(), want_c)
+        if kw["nxcorr_threshold"] is not None:
+            want_d, want_c = oracles.port.match(left, right, double=True, **kw)
+            disp, corr = handle.match(_cuda(left), _cuda(right), Config(double=True, **kw))
+            assert _same(disp.cpu().numpy(), want_d)
+            ok = ~np.isnan(want_c)
+            assert np.array_equal(np.isnan(corr.cpu().numpy()), ~ok)
+            assert np.max(np.abs(corr.cpu().numpy()[ok] - want_c[ok]), initial=0) <= 1e-12
+    valid = ~np.isnan(want_d)
+    assert valid.mean() > 0.2 or cols < 150, "wide test scenes should have valid matches"
+    # without the extension flag the reference's error stands
+    with pytest.raises(lb.BicosError, match="too large"):
+        handle.match(_cuda(left), _cuda(right), Config(mode_full=True))
 
 
 @pytest.mark.parametrize("rows,cols", [(1, 1), (1, 2), (2, 3), (3, 31), (1, 129), (2, 513), (1, 1025)])
@@ -405,8 +444,8 @@ def test_gpu_matches_golden_reference_outputs(handle, name):
     cols = left.shape[2]
     cfg = Config(**kw)
     l, r = _cuda(left), _cuda(right)
-    d0, k = handle.transform(l, cfg.mode_full)
-    d1, _ = handle.transform(r, cfg.mode_full)
+    d0, k = handle.transform(l, cfg.mode_full, cfg.wide_descriptors)
+    d1, _ = handle.transform(r, cfg.mode_full, cfg.wide_descriptors)
     assert np.array_equal(_words(d0, k, cols), g["desc0"]) and np.array_equal(_words(d1, k, cols), g["desc1"])
     keys = handle.search(d0, d1, k, cols, cfg.flags)
     disp, corr, raw = handle.refine(l, r, cfg, keys)

@@ -41,8 +41,9 @@ def test_port_matches_golden(oracles, name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     assert int(g["input_crc"]) == mg.crc(left, right), "synthetic generator changed: regenerate the fixtures"
     full = bool(kw.get("mode_full", False))
-    d0 = oracles.port.descriptors(left, full)
-    d1 = oracles.port.descriptors(right, full)
+    wide = bool(kw.get("wide_descriptors", False))
+    d0 = oracles.port.descriptors(left, full, wide)
+    d1 = oracles.port.descriptors(right, full, wide)
     assert np.array_equal(d0, g["desc0"]) and np.array_equal(d1, g["desc1"])
     flags = (2 | (1 if kw.get("no_dupes") else 0)) if kw.get("consistency") else 1
     raw = oracles.port.bicos(d0, d1, flags, kw.get("max_lr_diff", 1) if kw.get("consistency") else -1)
@@ -77,12 +78,34 @@ def test_port_matches_reference_build(oracles, n, dtype, full):
         assert (a[1] is None and b[1] is None) or _same(a[1], b[1])
 
 
+@pytest.mark.parametrize("n,dtype", [(17, np.uint8), (20, np.uint16), (21, np.uint16), (23, np.uint8)])
+def test_wide_extension_matches_reference_stage_templates(oracles, n, dtype):
+    """FULL stacks of 17..23 images need 258..486 bits; the reference's driver throws above 256. The port's
+    12- and 16-word paths are pinned against the reference's own stage templates with std::bitset<384/512>."""
+    if not oracles.ref.available():
+        pytest.skip("reference sources not present on this machine")
+    left, right, _ = synth.make_stacks(n, 512, 150, dtype, seed=n, row0=130, rows=16)
+    k = oracles.words_per_descriptor(n, True, wide=True)
+    assert k == (12 if n <= 20 else 16)
+    a, b = oracles.ref.descriptors(left, True, wide=True), oracles.port.descriptors(left, True, wide=True)
+    assert a.shape[2] == k and np.array_equal(a, b)
+    assert (b[..., 8:] != 0).any(), "the words beyond 256 bits must be in use"
+    for kw in (dict(nxcorr_threshold=None), dict(nxcorr_threshold=0.9, min_variance=2.0),
+               dict(nxcorr_threshold=0.8, subpixel_step=0.25, consistency=True, max_lr_diff=1, no_dupes=True)):
+        x = oracles.ref.match(left, right, mode_full=True, wide_descriptors=True, **kw)
+        y = oracles.port.match(left, right, mode_full=True, wide_descriptors=True, **kw)
+        assert _same(x[0], y[0])
+        assert (x[1] is None and y[1] is None) or _same(x[1], y[1])
+    with pytest.raises(RuntimeError, match="too large"):
+        oracles.port.match(left, right, mode_full=True)
+
+
 def test_search_ties_against_reference_build(oracles):
-    """Random low-entropy descriptors: many exact ties, all three flag combinations, K = 1..8."""
+    """Random low-entropy descriptors: many exact ties, all three flag combinations, K = 1..16."""
     if not oracles.ref.available():
         pytest.skip("reference sources not present on this machine")
     rng = np.random.default_rng(0)
-    for k in (1, 2, 4, 8):
+    for k in (1, 2, 4, 8, 12, 16):
         d0 = rng.integers(0, 8, size=(5, 90, k)).astype(np.uint32)
         d1 = rng.integers(0, 8, size=(5, 90, k)).astype(np.uint32)
         for flags in (1, 2, 3):

@@ -30,6 +30,9 @@ CONFIGS = {
     "metric": (33, np.uint8, 1536, 2048, C2, "BASELINE metric size, configs[1] Config"),
     "C3": (16, np.uint16, 2048, 2448, dict(nxcorr_threshold=0.96, min_variance=2.0, mode_full=True, double=True),
            "configs[2] at n=16 (largest FULL stack the reference accepts: 227 bits), double"),
+    "C3n20": (20, np.uint16, 2048, 2448, dict(nxcorr_threshold=0.96, min_variance=2.0, mode_full=True, double=True,
+                                              wide_descriptors=True),
+              "configs[2] as named: n=20 FULL = 363 bits -> 12-word descriptors (extension: the reference throws above 256 bits)"),
     "C4": (64, np.uint8, 3000, 4096, C1, "configs[3]: n=64 -> 250 bits -> 256-bit descriptors"),
     "C5": (33, np.uint8, 1200, 1920, C1, "configs[4]: one frame of the batch (frames are independent)"),
 }
@@ -67,11 +70,13 @@ def run_table(configs, iters=10, refcuda=None):
         valid = (~torch.isnan(disp) & (disp != -32768)).float().mean().item()
         line = {
             "config": name, "note": note, "n": n, "dtype": np.dtype(dt).name, "rows": rows, "cols": cols,
-            "K": lb.descriptor_words(n, cfg.mode_full), "cfg": kw, "ms_per_match": med, "ms_min": mn,
+            "K": lb.descriptor_words(n, cfg.mode_full, cfg.wide_descriptors), "cfg": kw, "ms_per_match": med, "ms_min": mn,
             "mpx_per_s": px / med / 1e3, "valid_frac": valid,
             "stage_ms": {k: v / max(cnt, 1) for k, v in zip(("transform_x2", "search", "refine"), stage_ms)},
         }
-        if refcuda is not None:
+        if refcuda is not None and kw.get("wide_descriptors"):
+            line["reference_cuda"] = {"error": "input stacks too large: the reference rejects more than 256 descriptor bits"}
+        elif refcuda is not None:
             ln, rn = l.cpu().numpy(), r.cpu().numpy()
             if dt == np.uint16:
                 ln, rn = ln.view(np.uint16), rn.view(np.uint16)
@@ -98,7 +103,7 @@ def run_table(configs, iters=10, refcuda=None):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="C1,C2,metric,C3,C4,C5")
+    ap.add_argument("--configs", default="C1,C2,metric,C3,C3n20,C4,C5")
     ap.add_argument("--iters", type=int, default=10)
     args = ap.parse_args()
     run_table(args.configs.split(","), args.iters)

@@ -25,6 +25,9 @@ constexpr int CHAINS = 8;
 #define FMUL2(x, y) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(y))
 #define FADD2(x, y) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(y))
 #define PRMT(x, y) asm volatile("prmt.b32 %0, %0, %1, 0x5410;" : "+r"(x) : "r"(y))
+#define IMADHI(x, y) asm volatile("mad.hi.u32 %0, %0, %1, %1;" : "+r"(x) : "r"(y))
+#define IMADWIDE(x2, x, y) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x2) : "r"(x), "r"(y))
+#define SHR(x, y) asm volatile("shr.u32 %0, %0, %1;" : "+r"(x) : "r"(y))
 #define DP4A(x, y) asm volatile("dp4a.u32.u32 %0, %0, %1, %0;" : "+r"(x) : "r"(y))
 
 template<int MODE>
@@ -66,6 +69,11 @@ __global__ void bench(uint32_t* out, long long* cycles, int iters, uint32_t seed
             if (MODE == 22) { DP4A(x[c], y); }
             if (MODE == 23) { FFMA2(x2[c], y2); LOP(x[c], y); }                 // packed fp32 + alu co-issue
             if (MODE == 24) { FFMA(x[c], y); LOP(x[c], y); }
+            if (MODE == 25) { IMADHI(x[c], y); }
+            if (MODE == 26) { IMADWIDE(x2[c], x[c], y); }
+            if (MODE == 27) { SHR(x[c], y); }
+            if (MODE == 28) { IMADHI(x[c], y); LOP(x[c], y); }
+            if (MODE == 29) { IMADWIDE(x2[c], x[c], y); LOP(x[c], y); }
             if (MODE == 15) { POPC(x[c]); POPC(x[c]); POPC(x[c]); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); MINU(x[c], y); MINU(x[c], y); IMAD(x[c], y); IMAD(x[c], y); IMAD(x[c], y); } // search-like
         }
     }
@@ -167,5 +175,10 @@ int main(int argc, char** argv) {
     run<22>("IDP4A", 1, sms, out, cyc);
     run<23>("FFMA2+LOP3", 2, sms, out, cyc);
     run<24>("FFMA+LOP3", 2, sms, out, cyc);
+    run<25>("IMAD.HI", 1, sms, out, cyc);
+    run<26>("IMAD.WIDE", 1, sms, out, cyc);
+    run<27>("SHR", 1, sms, out, cyc);
+    run<28>("IMAD.HI+LOP3", 2, sms, out, cyc);
+    run<29>("IMAD.WIDE+LOP3", 2, sms, out, cyc);
     return 0;
 }

@@ -27,7 +27,7 @@ static uint32_t rnd() {
 
 static std::vector<uint32_t> g_want, g_got; // shared by all instantiations of run()
 
-template<int K, int FLAGS, int A, int NT, int UNROLL>
+template<int K, int FLAGS, int A, int NT, int UNROLL, int MIX = DEFAULT_MIX<K>>
 void run(const char* name, Buffers& b, int schedule, bool is_reference = false) {
     const size_t key_bytes = b.px * 4 * sizeof(uint32_t);
     uint32_t *ff = b.keys, *fl = b.keys + b.px, *rf = b.keys + 2 * b.px, *rl = b.keys + 3 * b.px;
@@ -39,7 +39,7 @@ void run(const char* name, Buffers& b, int schedule, bool is_reference = false) 
     for (int it = 0; it < iters + 1; ++it) {
         CHECK(cudaMemset(b.keys, 0xFF, key_bytes));
         CHECK(cudaEventRecord(e0));
-        CHECK((launch_one<K, FLAGS, A, NT, UNROLL>(b.d0, b.d1, b.rows, b.cols, b.pitch, ff, fl, rf, rl, nullptr, schedule)));
+        CHECK((launch_one<K, FLAGS, A, NT, UNROLL, MIX>(b.d0, b.d1, b.rows, b.cols, b.pitch, ff, fl, rf, rl, nullptr, schedule)));
         CHECK(cudaEventRecord(e1));
         CHECK(cudaDeviceSynchronize());
         float ms;
@@ -111,6 +111,14 @@ void suite(int rows, int cols) {
     run<K, 2, 5, 128, 2>("A5 NT128 U2 auto", b, 0);
     run<K, 2, 3, 128, 2>("A3 NT128 U2 auto", b, 0);
     run<K, 2, 4, 128, 3>("A4 NT128 U3 x1", b, 1);
+    if constexpr (K >= 8) { // pairs per thread with one adder less and one POPC more (ALU / XU pipe balance)
+        run<K, 2, 4, 128, 2, 0>("A4 NT128 U2 auto MIX0", b, 0);
+        run<K, 2, 4, 128, 2, 1>("A4 NT128 U2 auto MIX1", b, 0);
+        run<K, 2, 4, 128, 2, 2>("A4 NT128 U2 auto MIX2", b, 0);
+        run<K, 2, 4, 128, 2, 3>("A4 NT128 U2 auto MIX3", b, 0);
+        run<K, 2, 5, 128, 2, 2>("A5 NT128 U2 auto MIX2", b, 0);
+        run<K, 2, 3, 128, 2, 1>("A3 NT128 U2 auto MIX1", b, 0);
+    }
     if constexpr (K <= 2) {
         run<K, 2, 8, 128, 2>("A8 NT128 U2 auto", b, 0);
         run<K, 2, 8, 128, 4>("A8 NT128 U4 auto", b, 0);
@@ -123,6 +131,12 @@ void suite(int rows, int cols) {
     run<K, 1, 4, 128, 2>("A4 NT128 U2 x2", b, 2);
     run<K, 1, 5, 128, 2>("A5 NT128 U2 auto", b, 0);
     run<K, 1, 3, 128, 2>("A3 NT128 U2 auto", b, 0);
+    if constexpr (K >= 8) {
+        run<K, 1, 4, 128, 2, 0>("A4 NT128 U2 auto MIX0", b, 0);
+        run<K, 1, 4, 128, 2, 1>("A4 NT128 U2 auto MIX1", b, 0);
+        run<K, 1, 4, 128, 2, 2>("A4 NT128 U2 auto MIX2", b, 0);
+        run<K, 1, 5, 128, 2, 2>("A5 NT128 U2 auto MIX2", b, 0);
+    }
     if constexpr (K <= 2) {
         run<K, 1, 8, 128, 2>("A8 NT128 U2 auto", b, 0);
         run<K, 1, 8, 128, 4>("A8 NT128 U4 auto", b, 0);
@@ -145,6 +159,10 @@ int main(int argc, char** argv) {
         suite<4>(rows, cols);
     else if (k == 8)
         suite<8>(rows, cols);
+    else if (k == 12)
+        suite<12>(rows, cols);
+    else if (k == 16)
+        suite<16>(rows, cols);
     else if (k == 2)
         suite<2>(rows, cols);
     else
