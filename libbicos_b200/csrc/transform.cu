@@ -285,11 +285,15 @@ __device__ __forceinline__ uint32_t fma_add(uint32_t x, uint32_t m, uint32_t y) 
     return r;
 }
 
-__device__ __forceinline__ uint32_t lt_u8x4(uint32_t a_nlo, uint32_t a, uint32_t b_lo, uint32_t b, uint32_t one) {
-    // bit 7 of every byte: a < b. a_nlo = ~a & 0x7f.., b_lo = b & 0x7f..
+// bit 7 of every byte: a < b, all other bits 0. Operands pre-split per plane: lo = p & 0x7f..,
+// nlo = ~p & 0x7f.., p7 = p & 0x80.., np7 = ~p & 0x80... The 7-bit sums cannot carry across lanes
+// (<= 254), bit 7 of t is the carry into the top bit, and maj(b7, ~a7, carry) is the carry out of
+// b + ~a = "a < b"; the pre-masked top bits keep every other result bit 0, so the caller can
+// accumulate results with shifts and adds, without masking.
+__device__ __forceinline__ uint32_t lt_u8x4(uint32_t a_nlo, uint32_t a_np7, uint32_t b_lo, uint32_t b_p7, uint32_t one) {
     uint32_t r;
-    const uint32_t t = fma_add(b_lo, one, a_nlo); // per byte <= 254: no carry across lanes
-    asm("lop3.b32 %0, %1, %2, %3, 0xb2;" : "=r"(r) : "r"(b), "r"(a), "r"(t)); // maj(b, ~a, t)
+    const uint32_t t = fma_add(b_lo, one, a_nlo);
+    asm("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(r) : "r"(b_p7), "r"(a_np7), "r"(t));
     return r;
 }
 
@@ -299,10 +303,13 @@ __device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t se
     return d;
 }
 
-template<int K>
+// EXACT: the stack has exactly 8K+1 images (9 / 17 / 33 / 65: the largest stack of each descriptor
+// width, and the common ones), so n is a compile-time constant: no load guards, no masking of
+// unused steps, the tail bits sit at a constant position and reuse the planes already loaded.
+template<int K, bool EXACT>
 __global__ void __launch_bounds__(THREADS) transform_limited_u8x4_kernel(
     const PlaneTable planes,
-    int n,
+    int n_runtime,
     int cols,
     size_t in_pitch,
     uint32_t* __restrict__ desc,
@@ -311,7 +318,8 @@ __global__ void __launch_bounds__(THREADS) transform_limited_u8x4_kernel(
     uint32_t minus_one
 ) {
     constexpr int NB = 8 * K + 1;
-    constexpr uint32_t LO7 = 0x7F7F7F7Fu, H16 = 0x80008000u, B16 = 0x00FF00FFu;
+    constexpr uint32_t LO7 = 0x7F7F7F7Fu, MSB = 0x80808080u, H16 = 0x80008000u, B16 = 0x00FF00FFu, C15 = 0x7FFF7FFFu;
+    const int n = EXACT ? NB : n_runtime;
     const int row = blockIdx.y;
     const int col = (blockIdx.x * THREADS + threadIdx.x) * 4;
     if (col >= cols)
@@ -323,81 +331,94 @@ __global__ void __launch_bounds__(THREADS) transform_limited_u8x4_kernel(
     for (int t = 0; t < NB; ++t)
         raw[t] = t < n ? __ldg(reinterpret_cast<const uint32_t*>(static_cast<const char*>(planes.p[t]) + row_off)) : 0u;
     raw[NB] = 0u;
-    const uint32_t ta = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const char*>(planes.p[n - 2]) + row_off));
-    const uint32_t tb = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const char*>(planes.p[n - 1]) + row_off));
-    uint32_t tpa = 0u, tpb = 0u;
-    if (n >= 4) {
-        tpa = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const char*>(planes.p[n - 4]) + row_off));
-        tpb = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const char*>(planes.p[n - 3]) + row_off));
+    uint32_t ta, tb, tpa = 0u, tpb = 0u;
+    if constexpr (EXACT) {
+        ta = raw[NB - 2];
+        tb = raw[NB - 1];
+        tpa = raw[NB - 4];
+        tpb = raw[NB - 3];
+    } else {
+        ta = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const char*>(planes.p[n - 2]) + row_off));
+        tb = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const char*>(planes.p[n - 1]) + row_off));
+        if (n >= 4) {
+            tpa = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const char*>(planes.p[n - 4]) + row_off));
+            tpb = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const char*>(planes.p[n - 3]) + row_off));
+        }
     }
 
-    // per-pixel sums in 16-bit lanes (even pixels 0,2 / odd pixels 1,3); padding planes are 0
-    uint32_t se = 0u, so = 0u;
+    // per-pixel sums: one IDP4A per pixel and plane (FMA pipe; the byte extraction it replaces was
+    // three ALU instructions per plane); padding planes are 0
+    uint32_t s0 = 0u, s1 = 0u, s2 = 0u, s3 = 0u;
 #pragma unroll
     for (int t = 0; t < NB; ++t) {
-        se = fma_add(raw[t] & B16, one, se);
-        so = fma_add((raw[t] >> 8) & B16, one, so);
+        s0 = __dp4a(raw[t], 0x00000001u, s0);
+        s1 = __dp4a(raw[t], 0x00000100u, s1);
+        s2 = __dp4a(raw[t], 0x00010000u, s2);
+        s3 = __dp4a(raw[t], 0x01000000u, s3);
     }
     // thr = ceil(sum / n) per pixel: p*n < sum  <=>  p < thr. Exact reciprocal multiply:
     // floor(x/n) == (x*m) >> 24 with m = ceil(2^24/n) for x < 2^15, n <= 65.
     const uint32_t m = ((1u << 24) + (uint32_t)n - 1u) / (uint32_t)n;
     const uint32_t nm1 = (uint32_t)n - 1u;
-    const uint32_t q0 = (((se & 0xFFFFu) + nm1) * m) >> 24, q2 = (((se >> 16) + nm1) * m) >> 24;
-    const uint32_t q1 = (((so & 0xFFFFu) + nm1) * m) >> 24, q3 = (((so >> 16) + nm1) * m) >> 24;
+    const uint32_t q0 = ((s0 + nm1) * m) >> 24, q1 = ((s1 + nm1) * m) >> 24;
+    const uint32_t q2 = ((s2 + nm1) * m) >> 24, q3 = ((s3 + nm1) * m) >> 24;
     const uint32_t thr = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
-    const uint32_t thr_lo = thr & LO7;
+    const uint32_t thr_lo = thr & LO7, thr_p7 = thr & MSB;
 
     uint32_t acc[4 * K];
 #pragma unroll
     for (int i = 0; i < 4 * K; ++i)
         acc[i] = 0u;
 
-    // bit7-of-each-byte result -> descriptor bit POS of the four pixels
+    // pre-masked bit-7 result -> descriptor bit POS of the four pixels (byte j of acc[POS / 8])
     auto put8 = [&](int pos, uint32_t r) {
-        const int sh = 7 - (pos & 7);
-        acc[pos >> 3] |= (r >> sh) & (0x01010101u << (pos & 7));
+        acc[pos >> 3] += r >> (7 - (pos & 7));
     };
-    // 16-bit-lane results (sign bit CLEAR means "less"; even word = pixels 0,2, odd word = pixels
-    // 1,3): one PRMT in sign-replication mode gathers the four sign bits as 0x00 / 0xFF bytes in
-    // pixel order, one LOP3 drops the complement into the bit position
+    // 16-bit-lane results (bit 15 SET means "less"; even word = pixels 0,2, odd word = pixels 1,3):
+    // one PRMT in sign-replication mode gathers the four flags as 0x00 / 0xFF bytes in pixel order,
+    // one LOP3 drops them into the bit position
     auto put16 = [&](int pos, uint32_t de, uint32_t dod) {
-        const uint32_t ge = prmt_b32(de, dod, 0xFBD9u); // byte j = 0xFF iff NOT less for pixel j
-        acc[pos >> 3] |= ~ge & (0x01010101u << (pos & 7));
+        const uint32_t g = prmt_b32(de, dod, 0xFBD9u);
+        acc[pos >> 3] |= g & (0x01010101u << (pos & 7));
     };
 
-    uint32_t lo_next = raw[0] & LO7, lo_next2 = raw[1] & LO7; // (b & 0x7f) of p[t+1], p[t+2]
-    uint32_t pe_prev2 = 0u, po_prev2 = 0u, pe_prev1 = 0u, po_prev1 = 0u; // ps(t-2) + 0x8000, ps(t-1) + 0x8000
-    uint32_t e_cur = raw[0] & B16, o_cur = (raw[0] >> 8) & B16;
+    // rolling per-plane splits of p[t], p[t+1] (p[t+2] is split in the iteration)
+    uint32_t lo_a = raw[0] & LO7, p7_a = raw[0] & MSB;
+    uint32_t lo_b = raw[1] & LO7, p7_b = raw[1] & MSB;
+    uint32_t np_prev2_e = 0u, np_prev2_o = 0u, np_prev1_e = 0u, np_prev1_o = 0u; // 0x7fff - ps(t-2), 0x7fff - ps(t-1), 16-bit lanes
+    uint32_t e_cur = raw[0] & B16, o_cur = prmt_b32(raw[0], 0u, 0x4341u);
 #pragma unroll
     for (int t = 0; t < NB - 2; ++t) {
         const int base = limited_base(t);
-        const uint32_t a = raw[t], b = raw[t + 1], c = raw[t + 2];
-        const uint32_t a_lo = lo_next;
-        const uint32_t b_lo = lo_next2;
-        const uint32_t c_lo = c & LO7;
-        lo_next = b_lo;
-        lo_next2 = c_lo;
-        const uint32_t a_nlo = a_lo ^ LO7;
-        put8(base + 0, lt_u8x4(a_nlo, a, b_lo, b, one)); // p[t] < p[t+1]
-        put8(base + 1, lt_u8x4(a_nlo, a, c_lo, c, one)); // p[t] < p[t+2]
-        put8(base + 2, lt_u8x4(a_nlo, a, thr_lo, thr, one)); // p[t]*n < sum
-        const uint32_t e_nxt = b & B16, o_nxt = (b >> 8) & B16;
+        const uint32_t b = raw[t + 1], c = raw[t + 2];
+        const uint32_t lo_c = c & LO7;
+        const uint32_t p7_c = fma_add(lo_c, minus_one, c); // c - (c & 0x7f..) == c & 0x80..
+        const uint32_t nlo_a = lo_a ^ LO7;
+        const uint32_t np7_a = fma_add(p7_a, minus_one, MSB); // 0x80.. - p7 == ~p & 0x80..
+        put8(base + 0, lt_u8x4(nlo_a, np7_a, lo_b, p7_b, one)); // p[t] < p[t+1]
+        put8(base + 1, lt_u8x4(nlo_a, np7_a, lo_c, p7_c, one)); // p[t] < p[t+2]
+        put8(base + 2, lt_u8x4(nlo_a, np7_a, thr_lo, thr_p7, one)); // p[t]*n < sum
+        const uint32_t e_nxt = b & B16, o_nxt = prmt_b32(b, 0u, 0x4341u);
         const uint32_t pe = fma_add(e_cur, one, e_nxt), po = fma_add(o_cur, one, o_nxt); // ps(t), 16-bit lanes, <= 510
-        if (t >= 2) // ps(t-2) < ps(t): the sign bit of ps(t-2) + 0x8000 - ps(t) stays set iff ps(t-2) >= ps(t)
-            put16(base + 3, fma_add(pe, minus_one, pe_prev2), fma_add(po, minus_one, po_prev2));
-        pe_prev2 = pe_prev1;
-        po_prev2 = po_prev1;
-        pe_prev1 = fma_add(pe, one, H16);
-        po_prev1 = fma_add(po, one, H16);
+        if (t >= 2) // ps(t-2) < ps(t): bit 15 of ps(t) + 0x7fff - ps(t-2) is set iff the difference is >= 1
+            put16(base + 3, fma_add(pe, one, np_prev2_e), fma_add(po, one, np_prev2_o));
+        np_prev2_e = np_prev1_e;
+        np_prev2_o = np_prev1_o;
+        np_prev1_e = fma_add(pe, minus_one, C15);
+        np_prev1_o = fma_add(po, minus_one, C15);
         e_cur = e_nxt;
         o_cur = o_nxt;
+        lo_a = lo_b;
+        p7_a = p7_b;
+        lo_b = lo_c;
+        p7_b = p7_c;
     }
 
     // tail bits (descriptor_transform.hpp:62-69), per pixel lanes
-    const uint32_t ta_nlo = (ta & LO7) ^ LO7;
-    const uint32_t r0 = lt_u8x4(ta_nlo, ta, tb & LO7, tb, one);
-    const uint32_t r1 = lt_u8x4(ta_nlo, ta, thr_lo, thr, one);
-    const uint32_t r2 = lt_u8x4((tb & LO7) ^ LO7, tb, thr_lo, thr, one);
+    const uint32_t ta_nlo = ~ta & LO7, ta_np7 = ~ta & MSB;
+    const uint32_t r0 = lt_u8x4(ta_nlo, ta_np7, tb & LO7, tb & MSB, one);
+    const uint32_t r1 = lt_u8x4(ta_nlo, ta_np7, thr_lo, thr_p7, one);
+    const uint32_t r2 = lt_u8x4(~tb & LO7, ~tb & MSB, thr_lo, thr_p7, one);
     const uint32_t ab_e = (ta & B16) + (tb & B16), ab_o = ((ta >> 8) & B16) + ((tb >> 8) & B16);
     const uint32_t pv_e = (tpa & B16) + (tpb & B16), pv_o = ((tpa >> 8) & B16) + ((tpb >> 8) & B16);
     // n < 4: the previous pair sum is -1, the bit is always set
@@ -541,7 +562,10 @@ cudaError_t launch_limited_k(
     const dim3 grid((cols + THREADS * PT - 1) / (THREADS * PT), rows);
     if constexpr (sizeof(TIn) == 1) {
         if (vec_ok) {
-            transform_limited_u8x4_kernel<K><<<grid, THREADS, 0, stream>>>(planes, n, cols, in_pitch, desc, desc_pitch_words, 1u, 0xFFFFFFFFu);
+            if (n == 8 * K + 1)
+                transform_limited_u8x4_kernel<K, true><<<grid, THREADS, 0, stream>>>(planes, n, cols, in_pitch, desc, desc_pitch_words, 1u, 0xFFFFFFFFu);
+            else
+                transform_limited_u8x4_kernel<K, false><<<grid, THREADS, 0, stream>>>(planes, n, cols, in_pitch, desc, desc_pitch_words, 1u, 0xFFFFFFFFu);
             return cudaGetLastError();
         }
     }
