@@ -13,12 +13,16 @@ variant = sys.argv[1] if len(sys.argv) > 1 else "config2"
 kw = dict(nxcorr_threshold=0.96, min_variance=2.0)
 if variant == "config2":
     kw.update(subpixel_step=0.1, consistency=True, max_lr_diff=1)
-l, r, _ = synth.make_stacks(33, 1536, 2048, np.uint8, xp=torch, device="cuda")
+if variant == "c4":  # 256-bit descriptors (n = 64), a row band of the 4096-column configuration
+    kw = dict(nxcorr_threshold=0.96, min_variance=2.0)
+    l, r, _ = synth.make_stacks(64, 3000, 4096, np.uint8, rows=256, xp=torch, device="cuda")
+else:
+    l, r, _ = synth.make_stacks(33, 1536, 2048, np.uint8, xp=torch, device="cuda")
 h = lb.Handle(0)
 cfg = lb.Config(**kw)
 out = h.match(l, r, cfg)
 torch.cuda.synchronize()
-for _ in range(2):
+for _ in range(0 if variant == "c4" else 2):
     h.match(l, r, cfg, out=out)
 torch.cuda.synchronize()
 print("ok", float(torch.nan_to_num(out[0]).sum()))
