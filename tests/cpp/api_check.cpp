@@ -5,7 +5,7 @@
 //
 //   api_check <in.bin> <out.bin> [sharded]
 //
-// in.bin : int32 n, rows, cols, depth(0=8U, 2=16U), mode, precision, variant, max_lr_diff, no_dupes;
+// in.bin : int32 n, rows, cols, depth(0=8U, 2=16U), mode (bit 0 FULL, bit 1 wide descriptors), precision, variant, max_lr_diff, no_dupes;
 //          float32 nxcorr_threshold, subpixel_step, min_variance (negative = unset);
 //          then stack0 and stack1 as dense [n][rows][cols] arrays
 // out.bin: int32 disparity type, corrmap type (0 = none), rows, cols; then both arrays, dense
@@ -76,7 +76,8 @@ int main(int argc, char** argv) {
     cfg.nxcorr_threshold = opt[0] >= 0 ? std::optional<float>(opt[0]) : std::nullopt;
     cfg.subpixel_step = opt[1] >= 0 ? std::optional<float>(opt[1]) : std::nullopt;
     cfg.min_variance = opt[2] >= 0 ? std::optional<float>(opt[2]) : std::nullopt;
-    cfg.mode = hdr[4] ? TransformMode::FULL : TransformMode::LIMITED;
+    cfg.mode = (hdr[4] & 1) ? TransformMode::FULL : TransformMode::LIMITED;
+    cfg.wide_descriptors = (hdr[4] & 2) != 0; // extension: 384 / 512-bit descriptors
     cfg.precision = hdr[5] ? Precision::DOUBLE : Precision::SINGLE;
     if (hdr[6])
         cfg.variant = Variant::Consistency { hdr[7], hdr[8] != 0 };

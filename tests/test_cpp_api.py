@@ -23,7 +23,8 @@ def _write_input(path, left, right, kw):
         return -1.0 if v is None else float(v)
 
     with open(path, "wb") as f:
-        f.write(struct.pack("<9i", n, rows, cols, depth, int(kw.get("mode_full", False)), int(kw.get("double", False)),
+        f.write(struct.pack("<9i", n, rows, cols, depth, int(kw.get("mode_full", False)) | (2 if kw.get("wide_descriptors") else 0),
+                            int(kw.get("double", False)),
                             int(kw.get("consistency", False)), int(kw.get("max_lr_diff", 1)),
                             int(kw.get("no_dupes", False))))
         f.write(struct.pack("<3f", opt(kw.get("nxcorr_threshold", 0.5)), opt(kw.get("subpixel_step")),
@@ -52,6 +53,7 @@ CASES = [
     (33, np.uint8, dict(nxcorr_threshold=0.96, min_variance=2.0, subpixel_step=0.1, consistency=True, max_lr_diff=1)),
     (16, np.uint16, dict(nxcorr_threshold=0.9, mode_full=True, double=True, min_variance=1.0)),
     (9, np.uint8, dict(nxcorr_threshold=None, consistency=True, max_lr_diff=2, no_dupes=True)),
+    (20, np.uint16, dict(nxcorr_threshold=0.9, mode_full=True, wide_descriptors=True, min_variance=1.0)),  # extension
 ]
 
 
