@@ -91,6 +91,44 @@ cudaError_t launch_search(
     cudaStream_t stream
 );
 
+// The two engines behind launch_search. `popc` (search.cu): XOR + POPC on the integer pipes, any
+// K and width. `mma` (search_mma.cu): the row's Hamming matrix as an int8 GEMM on the tensor
+// cores (tcgen05, TMEM accumulators) with the argmin as epilogue; K = 4/8/12/16 and rows of up
+// to 8192 pixels. Identical key arrays. launch_search picks by search_engine():
+// 0 = auto (mma where supported), 1 = popc, 2 = mma (error where unsupported).
+cudaError_t launch_search_popc(
+    const uint32_t* desc0,
+    const uint32_t* desc1,
+    int K,
+    int rows,
+    int cols,
+    size_t desc_pitch_words,
+    int flags,
+    uint32_t* fwd_first,
+    uint32_t* fwd_last,
+    uint32_t* rev_first,
+    uint32_t* rev_last,
+    cudaStream_t stream
+);
+cudaError_t launch_search_mma(
+    const uint32_t* desc0,
+    const uint32_t* desc1,
+    int K,
+    int rows,
+    int cols,
+    size_t desc_pitch_words,
+    int flags,
+    uint32_t* fwd_first,
+    uint32_t* fwd_last,
+    uint32_t* rev_first,
+    uint32_t* rev_last,
+    cudaStream_t stream
+);
+bool search_mma_supports(int K, int cols);
+int search_mma_smem_bytes(int K);
+int search_engine(); // initial value: environment BICOS_B200_SEARCH_ENGINE = auto | popc | mma
+void set_search_engine(int engine);
+
 // kernel 3: postfilter (no-duplicates / left-right consistency) fused with the NXC
 // agree / agree_subpixel refinement (reference a7 tail, a8, a9, a10, a11)
 cudaError_t launch_refine(

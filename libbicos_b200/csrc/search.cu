@@ -34,6 +34,10 @@
 
 #include "kernels.cuh"
 
+#include <atomic>
+#include <stdlib.h>
+#include <string.h>
+
 namespace bicos_b200 {
 namespace {
 
@@ -495,7 +499,7 @@ int search_smem_bytes(int K, int cols, int flags) {
     return bytes;
 }
 
-cudaError_t launch_search(
+cudaError_t launch_search_popc(
     const uint32_t* desc0,
     const uint32_t* desc1,
     int K,
@@ -526,6 +530,44 @@ cudaError_t launch_search(
             return launch_k<16>(desc0, desc1, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, stream);
     }
     return cudaErrorInvalidValue;
+}
+
+namespace {
+std::atomic<int> g_engine { -1 };
+}
+
+int search_engine() {
+    int e = g_engine.load(std::memory_order_relaxed);
+    if (e < 0) {
+        const char* v = getenv("BICOS_B200_SEARCH_ENGINE");
+        e = !v ? 1 : !strcmp(v, "auto") ? 0 : !strcmp(v, "mma") ? 2 : 1; // default popc until the tensor-core engine is validated on the device
+        g_engine.store(e, std::memory_order_relaxed);
+    }
+    return e;
+}
+
+void set_search_engine(int engine) {
+    g_engine.store(engine < 0 || engine > 2 ? 0 : engine, std::memory_order_relaxed);
+}
+
+cudaError_t launch_search(
+    const uint32_t* desc0,
+    const uint32_t* desc1,
+    int K,
+    int rows,
+    int cols,
+    size_t desc_pitch_words,
+    int flags,
+    uint32_t* fwd_first,
+    uint32_t* fwd_last,
+    uint32_t* rev_first,
+    uint32_t* rev_last,
+    cudaStream_t stream
+) {
+    const int engine = search_engine();
+    if (engine == 2 || (engine == 0 && search_mma_supports(K, cols)))
+        return launch_search_mma(desc0, desc1, K, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, stream);
+    return launch_search_popc(desc0, desc1, K, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, stream);
 }
 
 } // namespace bicos_b200

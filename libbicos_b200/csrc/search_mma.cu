@@ -1,0 +1,391 @@
+// Kernel 2 of the BICOS::match hot path, tensor-core engine: the W x W Hamming matrix of one
+// rectified row as an int8 GEMM on the 5th-generation tensor cores (tcgen05.mma kind::i8,
+// accumulators in TMEM), with the argmin as the epilogue. Same results, bit for bit, as the
+// popcount engine in search.cu.
+//
+// Replaces (behaviour, not structure):
+//   reference include/impl/cpu/bicos.hpp:29-76   ham / bicos_search
+//   reference include/impl/cuda/bicos.cuh:50-176 bicos_search / bicos_kernel[_smem]
+//
+// Why a GEMM is exact here: descriptor bit b of a left pixel becomes the int8 -64 (b = 1) or
+// +64 (b = 0), of a right pixel +64 (b = 1) or -64 (b = 0). A product is +4096 where the bits
+// differ and -4096 where they agree, so over KBITS positions
+//     acc(i, j) = 4096 * (2 * ham(i, j) - KBITS) = 8192 * ham(i, j) - 4096 * KBITS      (int32, exact)
+// and acc + column orders the pairs of a row by (ham, column) for rows of up to 8192 pixels:
+// the minimum over j is the reference's first strict minimum (bicos.hpp:57-60). acc + (8191 -
+// column) finds the last column at the minimal cost, whose difference from the first is the
+// no-duplicates test (bicos.hpp:62-71). The key needs ONE instruction per pair (add + min fused:
+// VIADDMNMX); the popcount engine needs 3 POPC + 6 LOP3 + 5 more for 128 bits.
+// The reverse search of the consistency check (bicos.hpp:99-106) is the same kernel with the
+// operands swapped (grid.y = 2): on the tensor cores the second W x W x KBITS product is
+// cheaper than column-wise minima of the first.
+//
+// One CTA = 128 left pixels of one row (the 128 TMEM lanes) against the whole right row in
+// tiles of 128 columns. 256 threads, three roles:
+//   warps 4-7  expand the packed right descriptors of the next tile to int8 in shared memory
+//              (128B-swizzled K-major, the layout TMA would produce); thread 128 then issues
+//              KBITS/32 tcgen05.mma (128 x 128 x 32) into one of two TMEM accumulators and
+//              commits to an mbarrier
+//   warps 0-3  expand the left tile once, then per tile: tcgen05.ld their lane quadrant, fold
+//              the 128 columns into the running minima, hand the accumulator back
+// Shared memory: (1 + 2) x KBITS/128 x 16 KB; TMEM: 2 x 128 columns.
+
+#include "kernels.cuh"
+
+#include <limits.h>
+
+namespace bicos_b200 {
+namespace {
+
+constexpr int TM = 128; // left pixels per CTA = TMEM lanes
+constexpr int TN = 128; // right pixels per accumulator
+constexpr int NTHREADS = 256;
+constexpr int ATOM_BYTES = 128 * 128; // 128 pixels x 128 descriptor bits as int8: 128-byte rows, one swizzle atom wide
+constexpr uint32_t TMEM_COLS = 2 * TN;
+constexpr int COL_BITS = 13; // acc steps by 8192 per unit of Hamming distance
+constexpr int COL_MAX = (1 << COL_BITS) - 1;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory"
+    );
+    return ok != 0;
+}
+
+// A wait that cannot hang the device: a pipeline bug traps (the launch then fails with an
+// error the C ABI reports) instead of spinning forever.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins)
+        if (spins > (1u << 20))
+            __trap();
+}
+
+__device__ __forceinline__ void fence_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32, M = 128, N = 128, K = 32
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory"
+    );
+}
+
+// 32 consecutive accumulator columns of this thread's lane; complete on return
+__device__ __forceinline__ void tc_load32(uint32_t taddr, int (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory"
+    );
+}
+
+// Shared-memory matrix descriptor (sm_100 format): K-major rows of 128 bytes, 128-byte swizzle,
+// groups of 8 rows 1024 bytes apart. `saddr` may point 32 * k bytes into the first row of a
+// 1024-byte aligned tile (the k-th 32-byte slice of K); the swizzle acts on address bits.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4); // start address
+    d |= (uint64_t)1 << 16; // leading byte offset: not used by swizzled K-major layouts
+    d |= (uint64_t)(1024 >> 4) << 32; // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46; // descriptor version
+    d |= (uint64_t)2 << 61; // SWIZZLE_128B
+    return d;
+}
+
+// instruction descriptor: D = s32, A = B = signed int8, both K-major, N = 128, M = 128
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+// four descriptor bits (an isolated nibble) -> four int8: the multiplication puts bit q on the
+// top bit of byte q without carries (4 x 4 distinct positions)
+template<bool RIGHT>
+__device__ __forceinline__ uint32_t expand4(uint32_t nibble) {
+    const uint32_t x = (nibble * 0x10204080u) & 0x80808080u;
+    return RIGHT ? (x ^ 0xC0C0C0C0u) : (x | 0x40404040u); // left: 1 -> -64, 0 -> +64; right: 1 -> +64, 0 -> -64
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// One pixel's K-word descriptor -> row r of K/4 swizzled int8 atoms starting at `tile`.
+template<int K, bool RIGHT>
+__device__ __forceinline__ void expand_pixel(const uint32_t* __restrict__ desc, uint32_t tile, int r) {
+    const uint32_t row = tile + (uint32_t)r * 128u;
+    const uint32_t sw = (uint32_t)(r & 7);
+#pragma unroll
+    for (int q = 0; q < K / 4; ++q) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(desc) + q);
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { // 16 bits -> one 16-byte chunk
+            const uint32_t h = w[c >> 1] >> (16 * (c & 1));
+            st_shared_v4(
+                row + (uint32_t)q * ATOM_BYTES + ((((uint32_t)c) ^ sw) << 4),
+                expand4<RIGHT>(h & 15u),
+                expand4<RIGHT>((h >> 4) & 15u),
+                expand4<RIGHT>((h >> 8) & 15u),
+                expand4<RIGHT>((h >> 12) & 15u)
+            );
+        }
+    }
+}
+
+struct MmaArgs {
+    const uint32_t* left;
+    const uint32_t* right;
+    int cols;
+    size_t pitch_words;
+    int mtiles; // ceil(cols / TM)
+    int ntiles; // ceil(cols / TN)
+    uint32_t* fwd_first; // blockIdx.y = 0: per left pixel over the right row
+    uint32_t* fwd_last;
+    uint32_t* rev_first; // blockIdx.y = 1: per right pixel over the left row
+    uint32_t* rev_last;
+};
+
+template<int K, bool NODUPES>
+__global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(const MmaArgs p) {
+    constexpr int KA = K / 4; // 128-bit atoms
+    constexpr int KBITS = 32 * K;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bars[4]; // accumulator full [2], accumulator drained [2]
+    __shared__ uint32_t tmem_base_slot;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int dir = blockIdx.y;
+    const int row = blockIdx.x / p.mtiles;
+    const int mt = blockIdx.x - row * p.mtiles;
+    const int cols = p.cols;
+    const uint32_t* const rows_of_d = (dir ? p.right : p.left) + (size_t)row * p.pitch_words;
+    const uint32_t* const cols_of_d = (dir ? p.left : p.right) + (size_t)row * p.pitch_words;
+
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t s_a = base;
+    const uint32_t s_b[2] = { base + KA * ATOM_BYTES, base + 2 * KA * ATOM_BYTES };
+    const uint32_t bar_full[2] = { smem_u32(&bars[0]), smem_u32(&bars[1]) };
+    const uint32_t bar_drained[2] = { smem_u32(&bars[2]), smem_u32(&bars[3]) };
+
+    if (tid == 0) {
+        mbar_init(bar_full[0], 1);
+        mbar_init(bar_full[1], 1);
+        mbar_init(bar_drained[0], TM);
+        mbar_init(bar_drained[1], TM);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    const int i = mt * TM + (tid & (TM - 1)); // this epilogue thread's pixel = its TMEM lane
+    if (tid < TM) {
+        expand_pixel<K, false>(rows_of_d + (size_t)min(i, cols - 1) * K, s_a, tid);
+        fence_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+
+    if (tid >= TM) {
+        // ---- producers: right tiles -> shared memory; thread 128 issues the MMAs ----
+        const int r = tid - TM;
+        for (int t = 0; t < p.ntiles; ++t) {
+            const int s = t & 1;
+            if (t >= 2)
+                mbar_wait(bar_full[s], ((t - 2) >> 1) & 1); // the MMAs that read this stage are done
+            const int j = min(t * TN + r, cols - 1);
+            expand_pixel<K, true>(cols_of_d + (size_t)j * K, s_b[s], r);
+            fence_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (r == 0) {
+                if (t >= 2)
+                    mbar_wait(bar_drained[s], ((t - 2) >> 1) & 1); // the epilogue has read this accumulator
+                tc_fence_after();
+#pragma unroll
+                for (int a = 0; a < KA; ++a)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        tc_mma_i8(
+                            tmem + (uint32_t)(s * TN),
+                            smem_desc(s_a + a * ATOM_BYTES + kk * 32),
+                            smem_desc(s_b[s] + a * ATOM_BYTES + kk * 32),
+                            IDESC,
+                            (a | kk) != 0
+                        );
+                tc_commit(bar_full[s]);
+            }
+        }
+    } else {
+        // ---- epilogue: running minima of acc + column over the row ----
+        int m_first = INT_MAX, m_last = INT_MAX;
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int t = 0; t < p.ntiles; ++t) {
+            const int s = t & 1;
+            mbar_wait(bar_full[s], (t >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < TN / 32; ++c) {
+                const int col0 = t * TN + c * 32;
+                if (col0 >= cols)
+                    break;
+                int v[32];
+                tc_load32(lane_base + (uint32_t)(s * TN + c * 32), v);
+                int f = INT_MAX, l = INT_MAX;
+                if (col0 + 32 <= cols) {
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) {
+                        f = min(f, v[u] + u);
+                        if constexpr (NODUPES)
+                            l = min(l, v[u] + (31 - u));
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) {
+                        if (col0 + u < cols) {
+                            f = min(f, v[u] + u);
+                            if constexpr (NODUPES)
+                                l = min(l, v[u] + (31 - u));
+                        }
+                    }
+                }
+                m_first = min(m_first, f + col0);
+                if constexpr (NODUPES)
+                    m_last = min(m_last, l + (COL_MAX - 31 - col0));
+            }
+            tc_fence_before();
+            mbar_arrive(bar_drained[s]);
+        }
+        if (i < cols) {
+            const size_t at = (size_t)row * cols + i;
+            const uint32_t f = (uint32_t)(m_first + 4096 * KBITS); // 8192 * cost + column
+            (dir ? p.rev_first : p.fwd_first)[at] = ((f >> COL_BITS) << 16) | (f & COL_MAX);
+            if constexpr (NODUPES) {
+                const uint32_t l = (uint32_t)(m_last + 4096 * KBITS); // 8192 * cost + 8191 - column
+                (dir ? p.rev_last : p.fwd_last)[at] = ((l >> COL_BITS) << 16) | ((65535u - COL_MAX) + (l & COL_MAX));
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+template<int K, bool NODUPES>
+cudaError_t launch_k(const MmaArgs& p, int rows, int dirs, cudaStream_t stream) {
+    const int smem = search_mma_smem_bytes(K);
+    auto kernel = search_mma_kernel<K, NODUPES>;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess)
+        return err;
+    const long long grid = (long long)rows * p.mtiles;
+    if (grid <= 0 || grid > 0x7FFFFFFFLL)
+        return cudaErrorInvalidConfiguration;
+    kernel<<<dim3((unsigned)grid, (unsigned)dirs), NTHREADS, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+} // namespace
+
+int search_mma_smem_bytes(int K) {
+    return 3 * (K / 4) * ATOM_BYTES + 1024; // left tile + two right stages + alignment slack
+}
+
+bool search_mma_supports(int K, int cols) {
+    return (K == 4 || K == 8 || K == 12 || K == 16) && cols >= 1 && cols <= COL_MAX + 1;
+}
+
+cudaError_t launch_search_mma(
+    const uint32_t* desc0,
+    const uint32_t* desc1,
+    int K,
+    int rows,
+    int cols,
+    size_t desc_pitch_words,
+    int flags,
+    uint32_t* fwd_first,
+    uint32_t* fwd_last,
+    uint32_t* rev_first,
+    uint32_t* rev_last,
+    cudaStream_t stream
+) {
+    if (rows <= 0 || !search_mma_supports(K, cols))
+        return cudaErrorInvalidValue;
+    MmaArgs p;
+    p.left = desc0;
+    p.right = desc1;
+    p.cols = cols;
+    p.pitch_words = desc_pitch_words;
+    p.mtiles = (cols + TM - 1) / TM;
+    p.ntiles = (cols + TN - 1) / TN;
+    p.fwd_first = fwd_first;
+    p.fwd_last = fwd_last;
+    p.rev_first = rev_first;
+    p.rev_last = rev_last;
+    const int dirs = (flags & FLAG_CONSISTENCY) ? 2 : 1;
+    const bool nodupes = (flags & FLAG_NODUPES) != 0;
+    switch (K) {
+        case 4:
+            return nodupes ? launch_k<4, true>(p, rows, dirs, stream) : launch_k<4, false>(p, rows, dirs, stream);
+        case 8:
+            return nodupes ? launch_k<8, true>(p, rows, dirs, stream) : launch_k<8, false>(p, rows, dirs, stream);
+        case 12:
+            return nodupes ? launch_k<12, true>(p, rows, dirs, stream) : launch_k<12, false>(p, rows, dirs, stream);
+        case 16:
+            return nodupes ? launch_k<16, true>(p, rows, dirs, stream) : launch_k<16, false>(p, rows, dirs, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+} // namespace bicos_b200
