@@ -39,7 +39,7 @@ namespace {
 
 constexpr int TM = 128; // left pixels per CTA = TMEM lanes
 constexpr int TN = 128; // right pixels per accumulator
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 288; // 4 epilogue warps, 4 producer warps, 1 MMA warp
 constexpr int ATOM_BYTES = 128 * 128; // 128 pixels x 128 descriptor bits as int8: 128-byte rows, one swizzle atom wide
 constexpr uint32_t TMEM_COLS = 2 * TN;
 constexpr int COL_BITS = 13; // acc steps by 8192 per unit of Hamming distance
@@ -110,20 +110,20 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint6
     );
 }
 
-// 32 consecutive accumulator columns of this thread's lane; complete on return
-__device__ __forceinline__ void tc_load32(uint32_t taddr, int (&v)[32]) {
+// 32 consecutive accumulator columns of this thread's lane. The load is asynchronous: the registers
+// are valid after tc_load32_wait on the same array (which takes them as in/out operands, so that
+// neither nvcc nor ptxas can move a use above the wait).
+__device__ __forceinline__ void tc_load32_issue(uint32_t taddr, int (&v)[32]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory"
     );
+}
+
+__device__ __forceinline__ void tc_load32_wait(int (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])::"memory");
 }
 
 // Shared-memory matrix descriptor (sm_100 format): K-major rows of 128 bytes, 128-byte swizzle,
@@ -153,15 +153,14 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// One pixel's K-word descriptor -> row r of K/4 swizzled int8 atoms starting at `tile`.
+// One pixel's descriptor (K / 4 uint4 in registers) -> row r of K/4 swizzled int8 atoms starting at `tile`.
 template<int K, bool RIGHT>
-__device__ __forceinline__ void expand_pixel(const uint32_t* __restrict__ desc, uint32_t tile, int r) {
+__device__ __forceinline__ void expand_pixel(const uint4 (&d)[K / 4], uint32_t tile, int r) {
     const uint32_t row = tile + (uint32_t)r * 128u;
     const uint32_t sw = (uint32_t)(r & 7);
 #pragma unroll
     for (int q = 0; q < K / 4; ++q) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(desc) + q);
-        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+        const uint32_t w[4] = { d[q].x, d[q].y, d[q].z, d[q].w };
 #pragma unroll
         for (int c = 0; c < 8; ++c) { // 16 bits -> one 16-byte chunk
             const uint32_t h = w[c >> 1] >> (16 * (c & 1));
@@ -174,6 +173,28 @@ __device__ __forceinline__ void expand_pixel(const uint32_t* __restrict__ desc, 
             );
         }
     }
+}
+
+template<int K>
+__device__ __forceinline__ void load_pixel(const uint32_t* __restrict__ desc, uint4 (&d)[K / 4]) {
+#pragma unroll
+    for (int q = 0; q < K / 4; ++q)
+        d[q] = __ldg(reinterpret_cast<const uint4*>(desc) + q);
+}
+
+// 32 accumulator columns folded into the running minima, four independent chains
+template<bool NODUPES>
+__device__ __forceinline__ void fold32(const int (&v)[32], int col0, int& m_first, int& m_last) {
+    int f[4] = { INT_MAX, INT_MAX, INT_MAX, INT_MAX }, l[4] = { INT_MAX, INT_MAX, INT_MAX, INT_MAX };
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+        f[u & 3] = min(f[u & 3], v[u] + u);
+        if constexpr (NODUPES)
+            l[u & 3] = min(l[u & 3], v[u] + (31 - u));
+    }
+    m_first = min(m_first, min(min(f[0], f[1]), min(f[2], f[3])) + col0);
+    if constexpr (NODUPES)
+        m_last = min(m_last, min(min(l[0], l[1]), min(l[2], l[3])) + (COL_MAX - 31 - col0));
 }
 
 struct MmaArgs {
@@ -189,12 +210,17 @@ struct MmaArgs {
     uint32_t* rev_last;
 };
 
+// right-tile stages in shared memory: as many as fit beside a second CTA (K <= 8) or alone
+template<int K>
+constexpr int STAGES = K == 4 ? 4 : K == 12 ? 3 : 2;
+
 template<int K, bool NODUPES>
 __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(const MmaArgs p) {
     constexpr int KA = K / 4; // 128-bit atoms
     constexpr int KBITS = 32 * K;
+    constexpr int NS = STAGES<K>;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bars[4]; // accumulator full [2], accumulator drained [2]
+    __shared__ uint64_t bars[2 * NS + 4]; // stage full [NS], stage free [NS], accumulator full [2], accumulator drained [2]
     __shared__ uint32_t tmem_base_slot;
 
     const int tid = threadIdx.x;
@@ -203,20 +229,26 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
     const int row = blockIdx.x / p.mtiles;
     const int mt = blockIdx.x - row * p.mtiles;
     const int cols = p.cols;
+    const int ntiles = p.ntiles;
     const uint32_t* const rows_of_d = (dir ? p.right : p.left) + (size_t)row * p.pitch_words;
     const uint32_t* const cols_of_d = (dir ? p.left : p.right) + (size_t)row * p.pitch_words;
 
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t s_a = base;
-    const uint32_t s_b[2] = { base + KA * ATOM_BYTES, base + 2 * KA * ATOM_BYTES };
-    const uint32_t bar_full[2] = { smem_u32(&bars[0]), smem_u32(&bars[1]) };
-    const uint32_t bar_drained[2] = { smem_u32(&bars[2]), smem_u32(&bars[3]) };
+    const uint32_t s_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t s_b = s_a + KA * ATOM_BYTES; // + stage * KA * ATOM_BYTES
+    const uint32_t bar_stage_full = smem_u32(&bars[0]); // + 8 * stage
+    const uint32_t bar_stage_free = bar_stage_full + 8 * NS;
+    const uint32_t bar_acc_full = bar_stage_free + 8 * NS; // + 8 * accumulator
+    const uint32_t bar_acc_drained = bar_acc_full + 16;
 
     if (tid == 0) {
-        mbar_init(bar_full[0], 1);
-        mbar_init(bar_full[1], 1);
-        mbar_init(bar_drained[0], TM);
-        mbar_init(bar_drained[1], TM);
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(bar_stage_full + 8 * s, TN);
+            mbar_init(bar_stage_free + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_acc_full + 8 * a, 1);
+            mbar_init(bar_acc_drained + 8 * a, TM);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -225,68 +257,100 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     const int i = mt * TM + (tid & (TM - 1)); // this epilogue thread's pixel = its TMEM lane
+    uint4 cur[KA];
     if (tid < TM) {
-        expand_pixel<K, false>(rows_of_d + (size_t)min(i, cols - 1) * K, s_a, tid);
+        load_pixel<K>(rows_of_d + (size_t)min(i, cols - 1) * K, cur);
+        expand_pixel<K, false>(cur, s_a, tid);
         fence_async_smem();
+    } else if (tid < TM + TN) {
+        load_pixel<K>(cols_of_d + (size_t)min(tid - TM, cols - 1) * K, cur); // first right tile, in flight across the barrier
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
 
-    if (tid >= TM) {
-        // ---- producers: right tiles -> shared memory; thread 128 issues the MMAs ----
-        const int r = tid - TM;
-        for (int t = 0; t < p.ntiles; ++t) {
-            const int s = t & 1;
-            if (t >= 2)
-                mbar_wait(bar_full[s], ((t - 2) >> 1) & 1); // the MMAs that read this stage are done
-            const int j = min(t * TN + r, cols - 1);
-            expand_pixel<K, true>(cols_of_d + (size_t)j * K, s_b[s], r);
-            fence_async_smem();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (r == 0) {
+    if (warp == 8) {
+        // ---- MMA issuer: one thread ----
+        if (tid == 8 * 32) {
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % NS, n = t / NS, a = t & 1;
+                mbar_wait(bar_stage_full + 8 * s, n & 1);
                 if (t >= 2)
-                    mbar_wait(bar_drained[s], ((t - 2) >> 1) & 1); // the epilogue has read this accumulator
+                    mbar_wait(bar_acc_drained + 8 * a, ((t - 2) >> 1) & 1); // the epilogue has read this accumulator
                 tc_fence_after();
+                const uint32_t sb = s_b + (uint32_t)(s * KA * ATOM_BYTES);
 #pragma unroll
-                for (int a = 0; a < KA; ++a)
+                for (int q = 0; q < KA; ++q)
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
                         tc_mma_i8(
-                            tmem + (uint32_t)(s * TN),
-                            smem_desc(s_a + a * ATOM_BYTES + kk * 32),
-                            smem_desc(s_b[s] + a * ATOM_BYTES + kk * 32),
+                            tmem + (uint32_t)(a * TN),
+                            smem_desc(s_a + q * ATOM_BYTES + kk * 32),
+                            smem_desc(sb + q * ATOM_BYTES + kk * 32),
                             IDESC,
-                            (a | kk) != 0
+                            (q | kk) != 0
                         );
-                tc_commit(bar_full[s]);
+                tc_commit(bar_stage_free + 8 * s);
+                tc_commit(bar_acc_full + 8 * a);
+            }
+        }
+    } else if (warp >= 4) {
+        // ---- producers: packed right descriptors -> int8 tiles in shared memory, one tile ahead in registers ----
+        const int r = tid - TM;
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % NS, n = t / NS;
+            uint4 nxt[KA];
+            if (t + 1 < ntiles)
+                load_pixel<K>(cols_of_d + (size_t)min((t + 1) * TN + r, cols - 1) * K, nxt);
+            if (t >= NS)
+                mbar_wait(bar_stage_free + 8 * s, (n - 1) & 1); // the MMAs that read this stage are done
+            expand_pixel<K, true>(cur, s_b + (uint32_t)(s * KA * ATOM_BYTES), r);
+            fence_async_smem();
+            mbar_arrive(bar_stage_full + 8 * s);
+            if (t + 1 < ntiles) {
+#pragma unroll
+                for (int q = 0; q < KA; ++q)
+                    cur[q] = nxt[q];
             }
         }
     } else {
         // ---- epilogue: running minima of acc + column over the row ----
         int m_first = INT_MAX, m_last = INT_MAX;
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        for (int t = 0; t < p.ntiles; ++t) {
-            const int s = t & 1;
-            mbar_wait(bar_full[s], (t >> 1) & 1);
+        for (int t = 0; t < ntiles; ++t) {
+            const int a = t & 1;
+            mbar_wait(bar_acc_full + 8 * a, (t >> 1) & 1);
             tc_fence_after();
+            const uint32_t acc = lane_base + (uint32_t)(a * TN);
+            const int tile0 = t * TN;
+            if (tile0 + TN <= cols) {
+                // whole tile: the next 32 columns are in flight while these are folded
+                int va[32], vb[32];
+                tc_load32_issue(acc, va);
+                tc_load32_wait(va);
+                tc_load32_issue(acc + 32, vb);
+                fold32<NODUPES>(va, tile0, m_first, m_last);
+                tc_load32_wait(vb);
+                tc_load32_issue(acc + 64, va);
+                fold32<NODUPES>(vb, tile0 + 32, m_first, m_last);
+                tc_load32_wait(va);
+                tc_load32_issue(acc + 96, vb);
+                fold32<NODUPES>(va, tile0 + 64, m_first, m_last);
+                tc_load32_wait(vb);
+                tc_fence_before();
+                mbar_arrive(bar_acc_drained + 8 * a); // the accumulator is in registers: hand it back before the last fold
+                fold32<NODUPES>(vb, tile0 + 96, m_first, m_last);
+            } else {
 #pragma unroll 1
-            for (int c = 0; c < TN / 32; ++c) {
-                const int col0 = t * TN + c * 32;
-                if (col0 >= cols)
-                    break;
-                int v[32];
-                tc_load32(lane_base + (uint32_t)(s * TN + c * 32), v);
-                int f = INT_MAX, l = INT_MAX;
-                if (col0 + 32 <= cols) {
-#pragma unroll
-                    for (int u = 0; u < 32; ++u) {
-                        f = min(f, v[u] + u);
-                        if constexpr (NODUPES)
-                            l = min(l, v[u] + (31 - u));
-                    }
-                } else {
+                for (int c = 0; c < TN / 32; ++c) {
+                    const int col0 = tile0 + c * 32;
+                    if (col0 >= cols)
+                        break;
+                    int v[32];
+                    tc_load32_issue(acc + (uint32_t)(c * 32), v);
+                    tc_load32_wait(v);
+                    int f = INT_MAX, l = INT_MAX;
 #pragma unroll
                     for (int u = 0; u < 32; ++u) {
                         if (col0 + u < cols) {
@@ -295,13 +359,13 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
                                 l = min(l, v[u] + (31 - u));
                         }
                     }
+                    m_first = min(m_first, f + col0);
+                    if constexpr (NODUPES)
+                        m_last = min(m_last, l + (COL_MAX - 31 - col0));
                 }
-                m_first = min(m_first, f + col0);
-                if constexpr (NODUPES)
-                    m_last = min(m_last, l + (COL_MAX - 31 - col0));
+                tc_fence_before();
+                mbar_arrive(bar_acc_drained + 8 * a);
             }
-            tc_fence_before();
-            mbar_arrive(bar_drained[s]);
         }
         if (i < cols) {
             const size_t at = (size_t)row * cols + i;
@@ -339,7 +403,8 @@ cudaError_t launch_k(const MmaArgs& p, int rows, int dirs, cudaStream_t stream) 
 } // namespace
 
 int search_mma_smem_bytes(int K) {
-    return 3 * (K / 4) * ATOM_BYTES + 1024; // left tile + two right stages + alignment slack
+    const int stages = K == 4 ? STAGES<4> : K == 8 ? STAGES<8> : K == 12 ? STAGES<12> : STAGES<16>;
+    return (1 + stages) * (K / 4) * ATOM_BYTES + 1024; // left tile + right stages + alignment slack
 }
 
 bool search_mma_supports(int K, int cols) {
