@@ -7,28 +7,36 @@
 //   reference include/impl/cpu/bicos.hpp:29-76   ham / bicos_search
 //   reference include/impl/cuda/bicos.cuh:50-176 bicos_search / bicos_kernel[_smem]
 //
-// Why a GEMM is exact here: descriptor bit b of a left pixel becomes the int8 -64 (b = 1) or
-// +64 (b = 0), of a right pixel +64 (b = 1) or -64 (b = 0). A product is +4096 where the bits
-// differ and -4096 where they agree, so over KBITS positions
-//     acc(i, j) = 4096 * (2 * ham(i, j) - KBITS) = 8192 * ham(i, j) - 4096 * KBITS      (int32, exact)
-// and acc + column orders the pairs of a row by (ham, column) for rows of up to 8192 pixels:
-// the minimum over j is the reference's first strict minimum (bicos.hpp:57-60). acc + (8191 -
-// column) finds the last column at the minimal cost, whose difference from the first is the
-// no-duplicates test (bicos.hpp:62-71). The key needs ONE instruction per pair (add + min fused:
-// VIADDMNMX); the popcount engine needs 3 POPC + 6 LOP3 + 5 more for 128 bits.
+// Why a GEMM is exact here. With a the left and b the right descriptor,
+//     ham(a, b) - popc(a) = #(a = 0, b = 1) - #(a = 1, b = 1) = sum_k b_k * (1 - 2 a_k).
+// Bit 8i + s of a 32-bit descriptor word becomes, in the right operand, the unsigned byte b * 2^s
+// (ONE instruction per four bytes: w & 0x01010101 << s; for s = 0 the byte is b * 128) and, in
+// the left operand, the signed byte (1 - 2a) * 2^(7 - s) (+-1 for s = 0). Every product is
+// +-128, so
+//     acc(i, j) = 128 * (ham(i, j) - popc(a_i))                                   (int32, exact)
+// and acc + u, u the column within the 128-column tile, orders the pairs of a tile by
+// (ham, column): the minimum is the reference's first strict minimum (bicos.hpp:57-60); acc +
+// (127 - u) finds the last column at the minimal cost, whose difference from the first is the
+// no-duplicates test (bicos.hpp:62-71). Tiles are merged as 8192 * (ham - popc) + column, which
+// is why rows of up to 8192 pixels are supported. For 128-bit descriptors |acc + u| < 2^15:
+// tcgen05.ld packs the low halves of two accumulator columns into one register and one
+// VIADDMNMX.S16x2 folds two pairs (the popcount engine needs 3 POPC + 6 LOP3 + 5 more per pair);
+// wider descriptors use the 32-bit VIADDMNMX, one pair per instruction.
 // The reverse search of the consistency check (bicos.hpp:99-106) is the same kernel with the
 // operands swapped (grid.y = 2): on the tensor cores the second W x W x KBITS product is
 // cheaper than column-wise minima of the first.
 //
 // One CTA = 128 left pixels of one row (the 128 TMEM lanes) against the whole right row in
-// tiles of 128 columns. 256 threads, three roles:
-//   warps 4-7  expand the packed right descriptors of the next tile to int8 in shared memory
-//              (128B-swizzled K-major, the layout TMA would produce); thread 128 then issues
-//              KBITS/32 tcgen05.mma (128 x 128 x 32) into one of two TMEM accumulators and
-//              commits to an mbarrier
-//   warps 0-3  expand the left tile once, then per tile: tcgen05.ld their lane quadrant, fold
-//              the 128 columns into the running minima, hand the accumulator back
-// Shared memory: (1 + 2) x KBITS/128 x 16 KB; TMEM: 2 x 128 columns.
+// tiles of 128 columns. 288 threads, three roles:
+//   warps 4-7  producers: packed right descriptors of a tile -> uint8 in shared memory
+//              (128B-swizzled K-major, the layout TMA would produce), 2-4 stages, the next
+//              tile's descriptors already in registers
+//   warp 8     one thread issues KBITS/32 tcgen05.mma (128 x 128 x 32, kind::i8) per tile into one
+//              of two TMEM accumulators and commits to the stage / accumulator mbarriers
+//   warps 0-3  expand the left tile once, then per tile: tcgen05.ld their lane quadrant (the next
+//              half in flight while one is folded), fold it into the running minima, hand the
+//              accumulator back
+// Shared memory: (1 + stages) x KBITS/128 x 16 KB; TMEM: 2 x 128 columns.
 
 #include "kernels.cuh"
 
@@ -42,7 +50,7 @@ constexpr int TN = 128; // right pixels per accumulator
 constexpr int NTHREADS = 288; // 4 epilogue warps, 4 producer warps, 1 MMA warp
 constexpr int ATOM_BYTES = 128 * 128; // 128 pixels x 128 descriptor bits as int8: 128-byte rows, one swizzle atom wide
 constexpr uint32_t TMEM_COLS = 2 * TN;
-constexpr int COL_BITS = 13; // acc steps by 8192 per unit of Hamming distance
+constexpr int COL_BITS = 13; // merged keys step by 8192 per unit of Hamming distance
 constexpr int COL_MAX = (1 << COL_BITS) - 1;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -122,6 +130,16 @@ __device__ __forceinline__ void tc_load32_issue(uint32_t taddr, int (&v)[32]) {
     );
 }
 
+// 64 consecutive columns, the low 16 bits of columns 2r and 2r + 1 packed into register r
+__device__ __forceinline__ void tc_load64_packed_issue(uint32_t taddr, int (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory"
+    );
+}
+
 __device__ __forceinline__ void tc_load32_wait(int (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])::"memory");
 }
@@ -138,22 +156,32 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
     return d;
 }
 
-// instruction descriptor: D = s32, A = B = signed int8, both K-major, N = 128, M = 128
-constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-
-// four descriptor bits (an isolated nibble) -> four int8: the multiplication puts bit q on the
-// top bit of byte q without carries (4 x 4 distinct positions)
-template<bool RIGHT>
-__device__ __forceinline__ uint32_t expand4(uint32_t nibble) {
-    const uint32_t x = (nibble * 0x10204080u) & 0x80808080u;
-    return RIGHT ? (x ^ 0xC0C0C0C0u) : (x | 0x40404040u); // left: 1 -> -64, 0 -> +64; right: 1 -> +64, 0 -> -64
-}
+// instruction descriptor: D = s32, A = signed int8, B = unsigned int8, both K-major, N = 128, M = 128
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// One pixel's descriptor (K / 4 uint4 in registers) -> row r of K/4 swizzled int8 atoms starting at `tile`.
+// Bits s, 8 + s, 16 + s, 24 + s of a descriptor word -> four operand bytes (see the header).
+template<bool RIGHT, int S>
+__device__ __forceinline__ uint32_t expand_word(uint32_t w) {
+    if constexpr (RIGHT) {
+        if constexpr (S == 0)
+            return (w << 7) & 0x80808080u; // b * 128
+        else
+            return w & (0x01010101u << S); // b * 2^S
+    } else {
+        constexpr int P = S == 0 ? 0 : 7 - S; // magnitude 2^P
+        constexpr uint32_t MAG = 0x01010101u << P;
+        constexpr uint32_t HIGH = 0x01010101u * ((0xFFu << (P + 1)) & 0xFFu); // -2^P = 2^P | HIGH, per byte
+        const uint32_t neg = ((w >> S) & 0x01010101u) * 0xFFu; // 0xFF where the bit is set
+        return (neg & HIGH) | MAG;
+    }
+}
+
+// One pixel's descriptor (K / 4 uint4 in registers) -> row r of K/4 swizzled atoms starting at `tile`.
+// Word wi of an atom fills the 16-byte chunks 2 wi (s = 0..3) and 2 wi + 1 (s = 4..7).
 template<int K, bool RIGHT>
 __device__ __forceinline__ void expand_pixel(const uint4 (&d)[K / 4], uint32_t tile, int r) {
     const uint32_t row = tile + (uint32_t)r * 128u;
@@ -162,14 +190,20 @@ __device__ __forceinline__ void expand_pixel(const uint4 (&d)[K / 4], uint32_t t
     for (int q = 0; q < K / 4; ++q) {
         const uint32_t w[4] = { d[q].x, d[q].y, d[q].z, d[q].w };
 #pragma unroll
-        for (int c = 0; c < 8; ++c) { // 16 bits -> one 16-byte chunk
-            const uint32_t h = w[c >> 1] >> (16 * (c & 1));
+        for (int wi = 0; wi < 4; ++wi) {
             st_shared_v4(
-                row + (uint32_t)q * ATOM_BYTES + ((((uint32_t)c) ^ sw) << 4),
-                expand4<RIGHT>(h & 15u),
-                expand4<RIGHT>((h >> 4) & 15u),
-                expand4<RIGHT>((h >> 8) & 15u),
-                expand4<RIGHT>((h >> 12) & 15u)
+                row + (uint32_t)q * ATOM_BYTES + ((((uint32_t)(2 * wi)) ^ sw) << 4),
+                expand_word<RIGHT, 0>(w[wi]),
+                expand_word<RIGHT, 1>(w[wi]),
+                expand_word<RIGHT, 2>(w[wi]),
+                expand_word<RIGHT, 3>(w[wi])
+            );
+            st_shared_v4(
+                row + (uint32_t)q * ATOM_BYTES + ((((uint32_t)(2 * wi + 1)) ^ sw) << 4),
+                expand_word<RIGHT, 4>(w[wi]),
+                expand_word<RIGHT, 5>(w[wi]),
+                expand_word<RIGHT, 6>(w[wi]),
+                expand_word<RIGHT, 7>(w[wi])
             );
         }
     }
@@ -182,19 +216,86 @@ __device__ __forceinline__ void load_pixel(const uint32_t* __restrict__ desc, ui
         d[q] = __ldg(reinterpret_cast<const uint4*>(desc) + q);
 }
 
-// 32 accumulator columns folded into the running minima, four independent chains
-template<bool NODUPES>
-__device__ __forceinline__ void fold32(const int (&v)[32], int col0, int& m_first, int& m_last) {
-    int f[4] = { INT_MAX, INT_MAX, INT_MAX, INT_MAX }, l[4] = { INT_MAX, INT_MAX, INT_MAX, INT_MAX };
+// Running minima of one 128-column tile: acc + u (first) and acc + 127 - u (last), u the column
+// within the tile, in four independent chains. Packed: two 16-bit lanes per register.
+struct TileMin32 {
+    int f[4], l[4];
+    __device__ __forceinline__ TileMin32() {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            f[c] = l[c] = INT_MAX;
+    }
+};
+
+struct TileMin16 {
+    uint32_t f[4], l[4];
+    __device__ __forceinline__ TileMin16() {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            f[c] = l[c] = 0x7FFF7FFFu;
+    }
+};
+
+// 32 accumulator columns starting at tile column U0
+template<bool NODUPES, int U0>
+__device__ __forceinline__ void fold32(const int (&v)[32], TileMin32& m) {
 #pragma unroll
     for (int u = 0; u < 32; ++u) {
-        f[u & 3] = min(f[u & 3], v[u] + u);
+        m.f[u & 3] = min(m.f[u & 3], v[u] + (U0 + u));
         if constexpr (NODUPES)
-            l[u & 3] = min(l[u & 3], v[u] + (31 - u));
+            m.l[u & 3] = min(m.l[u & 3], v[u] + (127 - U0 - u));
     }
-    m_first = min(m_first, min(min(f[0], f[1]), min(f[2], f[3])) + col0);
+}
+
+// the same with a run-time bound: columns from `valid` on do not exist
+template<bool NODUPES>
+__device__ __forceinline__ void fold32_guarded(const int (&v)[32], int u0, int valid, TileMin32& m) {
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+        if (u0 + u < valid) {
+            m.f[u & 3] = min(m.f[u & 3], v[u] + (u0 + u));
+            if constexpr (NODUPES)
+                m.l[u & 3] = min(m.l[u & 3], v[u] + (127 - u0 - u));
+        }
+    }
+}
+
+// 64 accumulator columns starting at tile column U0, low halves packed two per register
+template<bool NODUPES, int U0>
+__device__ __forceinline__ void fold64_packed(const int (&v)[32], TileMin16& m) {
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        constexpr uint32_t ONE = 0x00010001u;
+        const uint32_t uf = (uint32_t)(U0 + 2 * r) * ONE + 0x00010000u; // columns U0 + 2r | U0 + 2r + 1
+        const uint32_t ul = (uint32_t)(127 - U0 - 2 * r) * ONE - 0x00010000u; // 127 - column
+        m.f[r & 3] = __viaddmin_s16x2((uint32_t)v[r], uf, m.f[r & 3]);
+        if constexpr (NODUPES)
+            m.l[r & 3] = __viaddmin_s16x2((uint32_t)v[r], ul, m.l[r & 3]);
+    }
+}
+
+// tile minimum t = 128 * (ham - popc) + u  ->  8192 * (ham - popc) + u
+__device__ __forceinline__ int widen_key(int t) {
+    return ((t & ~127) << 6) + (t & 127);
+}
+
+template<bool NODUPES>
+__device__ __forceinline__ void merge_tile(const TileMin32& m, int tile0, int& m_first, int& m_last) {
+    m_first = min(m_first, widen_key(min(min(m.f[0], m.f[1]), min(m.f[2], m.f[3]))) + tile0);
     if constexpr (NODUPES)
-        m_last = min(m_last, min(min(l[0], l[1]), min(l[2], l[3])) + (COL_MAX - 31 - col0));
+        m_last = min(m_last, widen_key(min(min(m.l[0], m.l[1]), min(m.l[2], m.l[3]))) + (COL_MAX - 127 - tile0));
+}
+
+__device__ __forceinline__ int min_of_lanes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    const uint32_t m = __vmins2(__vmins2(a, b), __vmins2(c, d));
+    return min((int)(short)(m & 0xFFFFu), (int)(short)(m >> 16));
+}
+
+template<bool NODUPES>
+__device__ __forceinline__ void merge_tile(const TileMin16& m, int tile0, int& m_first, int& m_last) {
+    m_first = min(m_first, widen_key(min_of_lanes(m.f[0], m.f[1], m.f[2], m.f[3])) + tile0);
+    if constexpr (NODUPES)
+        m_last = min(m_last, widen_key(min_of_lanes(m.l[0], m.l[1], m.l[2], m.l[3])) + (COL_MAX - 127 - tile0));
 }
 
 struct MmaArgs {
@@ -217,7 +318,6 @@ constexpr int STAGES = K == 4 ? 4 : K == 12 ? 3 : 2;
 template<int K, bool NODUPES>
 __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(const MmaArgs p) {
     constexpr int KA = K / 4; // 128-bit atoms
-    constexpr int KBITS = 32 * K;
     constexpr int NS = STAGES<K>;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bars[2 * NS + 4]; // stage full [NS], stage free [NS], accumulator full [2], accumulator drained [2]
@@ -258,10 +358,14 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
     }
     const int i = mt * TM + (tid & (TM - 1)); // this epilogue thread's pixel = its TMEM lane
     uint4 cur[KA];
+    int pa = 0; // popcount of this thread's own (left) descriptor
     if (tid < TM) {
         load_pixel<K>(rows_of_d + (size_t)min(i, cols - 1) * K, cur);
         expand_pixel<K, false>(cur, s_a, tid);
         fence_async_smem();
+#pragma unroll
+        for (int q = 0; q < KA; ++q)
+            pa += __popc(cur[q].x) + __popc(cur[q].y) + __popc(cur[q].z) + __popc(cur[q].w);
     } else if (tid < TM + TN) {
         load_pixel<K>(cols_of_d + (size_t)min(tid - TM, cols - 1) * K, cur); // first right tile, in flight across the barrier
     }
@@ -315,7 +419,7 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
             }
         }
     } else {
-        // ---- epilogue: running minima of acc + column over the row ----
+        // ---- epilogue: running minima of 8192 * (ham - popc) + column over the row ----
         int m_first = INT_MAX, m_last = INT_MAX;
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
         for (int t = 0; t < ntiles; ++t) {
@@ -324,57 +428,57 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
             tc_fence_after();
             const uint32_t acc = lane_base + (uint32_t)(a * TN);
             const int tile0 = t * TN;
-            if (tile0 + TN <= cols) {
-                // whole tile: the next 32 columns are in flight while these are folded
-                int va[32], vb[32];
-                tc_load32_issue(acc, va);
-                tc_load32_wait(va);
-                tc_load32_issue(acc + 32, vb);
-                fold32<NODUPES>(va, tile0, m_first, m_last);
-                tc_load32_wait(vb);
-                tc_load32_issue(acc + 64, va);
-                fold32<NODUPES>(vb, tile0 + 32, m_first, m_last);
-                tc_load32_wait(va);
-                tc_load32_issue(acc + 96, vb);
-                fold32<NODUPES>(va, tile0 + 64, m_first, m_last);
-                tc_load32_wait(vb);
-                tc_fence_before();
-                mbar_arrive(bar_acc_drained + 8 * a); // the accumulator is in registers: hand it back before the last fold
-                fold32<NODUPES>(vb, tile0 + 96, m_first, m_last);
-            } else {
+            int va[32], vb[32];
+            if (tile0 + TN > cols) {
+                // ragged last tile
+                TileMin32 m;
 #pragma unroll 1
-                for (int c = 0; c < TN / 32; ++c) {
-                    const int col0 = tile0 + c * 32;
-                    if (col0 >= cols)
-                        break;
-                    int v[32];
-                    tc_load32_issue(acc + (uint32_t)(c * 32), v);
-                    tc_load32_wait(v);
-                    int f = INT_MAX, l = INT_MAX;
-#pragma unroll
-                    for (int u = 0; u < 32; ++u) {
-                        if (col0 + u < cols) {
-                            f = min(f, v[u] + u);
-                            if constexpr (NODUPES)
-                                l = min(l, v[u] + (31 - u));
-                        }
-                    }
-                    m_first = min(m_first, f + col0);
-                    if constexpr (NODUPES)
-                        m_last = min(m_last, l + (COL_MAX - 31 - col0));
+                for (int u0 = 0; u0 < TN && tile0 + u0 < cols; u0 += 32) {
+                    tc_load32_issue(acc + (uint32_t)u0, va);
+                    tc_load32_wait(va);
+                    fold32_guarded<NODUPES>(va, u0, cols - tile0, m);
                 }
                 tc_fence_before();
                 mbar_arrive(bar_acc_drained + 8 * a);
+                merge_tile<NODUPES>(m, tile0, m_first, m_last);
+            } else if constexpr (K == 4) {
+                // 16-bit lanes: the second 64 columns are in flight while the first are folded
+                TileMin16 m;
+                tc_load64_packed_issue(acc, va);
+                tc_load32_wait(va);
+                tc_load64_packed_issue(acc + 64, vb);
+                fold64_packed<NODUPES, 0>(va, m);
+                tc_load32_wait(vb);
+                tc_fence_before();
+                mbar_arrive(bar_acc_drained + 8 * a); // the accumulator is in registers: hand it back before the last fold
+                fold64_packed<NODUPES, 64>(vb, m);
+                merge_tile<NODUPES>(m, tile0, m_first, m_last);
+            } else {
+                TileMin32 m;
+                tc_load32_issue(acc, va);
+                tc_load32_wait(va);
+                tc_load32_issue(acc + 32, vb);
+                fold32<NODUPES, 0>(va, m);
+                tc_load32_wait(vb);
+                tc_load32_issue(acc + 64, va);
+                fold32<NODUPES, 32>(vb, m);
+                tc_load32_wait(va);
+                tc_load32_issue(acc + 96, vb);
+                fold32<NODUPES, 64>(va, m);
+                tc_load32_wait(vb);
+                tc_fence_before();
+                mbar_arrive(bar_acc_drained + 8 * a);
+                fold32<NODUPES, 96>(vb, m);
+                merge_tile<NODUPES>(m, tile0, m_first, m_last);
             }
         }
         if (i < cols) {
             const size_t at = (size_t)row * cols + i;
-            const uint32_t f = (uint32_t)(m_first + 4096 * KBITS); // 8192 * cost + column
-            (dir ? p.rev_first : p.fwd_first)[at] = ((f >> COL_BITS) << 16) | (f & COL_MAX);
-            if constexpr (NODUPES) {
-                const uint32_t l = (uint32_t)(m_last + 4096 * KBITS); // 8192 * cost + 8191 - column
-                (dir ? p.rev_last : p.fwd_last)[at] = ((l >> COL_BITS) << 16) | ((65535u - COL_MAX) + (l & COL_MAX));
-            }
+            // m = 8192 * (cost - popc) + column: arithmetic shift = floor, the low bits are the column
+            (dir ? p.rev_first : p.fwd_first)[at] = ((uint32_t)(pa + (m_first >> COL_BITS)) << 16) | ((uint32_t)m_first & COL_MAX);
+            if constexpr (NODUPES)
+                (dir ? p.rev_last : p.fwd_last)[at] =
+                    ((uint32_t)(pa + (m_last >> COL_BITS)) << 16) | ((65535u - COL_MAX) + ((uint32_t)m_last & COL_MAX));
         }
     }
 
