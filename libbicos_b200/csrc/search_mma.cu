@@ -47,7 +47,7 @@ namespace {
 
 constexpr int TM = 128; // left pixels per CTA = TMEM lanes
 constexpr int TN = 128; // right pixels per accumulator
-constexpr int NTHREADS = 288; // 4 epilogue warps, 4 producer warps, 1 MMA warp
+constexpr int NTHREADS = 320; // 4 epilogue warps, 4 producer warps, 1 MMA warp, 1 loader warp
 constexpr int ATOM_BYTES = 128 * 128; // 128 pixels x 128 descriptor bits as int8: 128-byte rows, one swizzle atom wide
 constexpr uint32_t TMEM_COLS = 2 * TN;
 constexpr int COL_BITS = 13; // merged keys step by 8192 per unit of Hamming distance
@@ -86,6 +86,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins)
         if (spins > (1u << 20))
             __trap();
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+// TMA bulk copy global -> shared (contiguous bytes, 16-byte granular), completion counted on `bar`
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 
 __device__ __forceinline__ void fence_async_smem() {
@@ -301,44 +318,78 @@ __device__ __forceinline__ void merge_tile(const TileMin16& m, int tile0, int& m
 struct MmaArgs {
     const uint32_t* left;
     const uint32_t* right;
-    int cols;
+    int rows, cols;
     size_t pitch_words;
     int mtiles; // ceil(cols / TM)
     int ntiles; // ceil(cols / TN)
-    uint32_t* fwd_first; // blockIdx.y = 0: per left pixel over the right row
+    long long items; // directions x rows x mtiles
+    uint32_t* fwd_first; // direction 0: per left pixel over the right row
     uint32_t* fwd_last;
-    uint32_t* rev_first; // blockIdx.y = 1: per right pixel over the left row
+    uint32_t* rev_first; // direction 1: per right pixel over the left row
     uint32_t* rev_last;
 };
 
-// right-tile stages in shared memory: as many as fit beside a second CTA (K <= 8) or alone
+// right-tile stages and left-tile buffers in shared memory: what fits beside a second CTA (K <= 8) or alone
 template<int K>
 constexpr int STAGES = K == 4 ? 4 : K == 12 ? 3 : 2;
+template<int K>
+constexpr int LEFT_BUFFERS = K == 4 ? 2 : 1;
+// ring of packed right tiles (TN descriptors as they lie in global memory), filled by TMA bulk copies
+template<int K>
+constexpr int PACKED_STAGES = K == 4 ? 4 : K == 8 ? 3 : 2;
+
+// A work item = 128 pixels (M tile `mt`) of one row in one direction against the whole other row.
+// Items are numbered direction-major, then row, then M tile; a CTA walks a contiguous range.
+struct Item {
+    int dir, row, mt;
+    __device__ __forceinline__ void decode(long long item, int rows, int mtiles) {
+        const long long per_dir = (long long)rows * mtiles;
+        dir = (int)(item / per_dir);
+        const int rem = (int)(item - dir * per_dir);
+        row = rem / mtiles;
+        mt = rem - row * mtiles;
+    }
+    __device__ __forceinline__ void next(int rows, int mtiles) {
+        if (++mt == mtiles) {
+            mt = 0;
+            if (++row == rows) {
+                row = 0;
+                ++dir;
+            }
+        }
+    }
+};
 
 template<int K, bool NODUPES>
 __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(const MmaArgs p) {
     constexpr int KA = K / 4; // 128-bit atoms
     constexpr int NS = STAGES<K>;
+    constexpr int NA = LEFT_BUFFERS<K>;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bars[2 * NS + 4]; // stage full [NS], stage free [NS], accumulator full [2], accumulator drained [2]
+    constexpr int NP = PACKED_STAGES<K>;
+    constexpr int PACKED_BYTES = TN * K * 4;
+    // stage full [NS], stage free [NS], accumulator full [2], accumulator drained [2], left tile full [NA],
+    // packed full [NP], packed free [NP]
+    __shared__ uint64_t bars[2 * NS + 4 + NA + 2 * NP];
     __shared__ uint32_t tmem_base_slot;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
-    const int dir = blockIdx.y;
-    const int row = blockIdx.x / p.mtiles;
-    const int mt = blockIdx.x - row * p.mtiles;
     const int cols = p.cols;
     const int ntiles = p.ntiles;
-    const uint32_t* const rows_of_d = (dir ? p.right : p.left) + (size_t)row * p.pitch_words;
-    const uint32_t* const cols_of_d = (dir ? p.left : p.right) + (size_t)row * p.pitch_words;
+    const long long item0 = p.items * blockIdx.x / gridDim.x;
+    const int nitems = (int)(p.items * (blockIdx.x + 1) / gridDim.x - item0);
 
-    const uint32_t s_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t s_b = s_a + KA * ATOM_BYTES; // + stage * KA * ATOM_BYTES
+    const uint32_t s_a = (smem_u32(smem_raw) + 1023u) & ~1023u; // + buffer * KA * ATOM_BYTES
+    const uint32_t s_b = s_a + NA * KA * ATOM_BYTES; // + stage * KA * ATOM_BYTES
     const uint32_t bar_stage_full = smem_u32(&bars[0]); // + 8 * stage
     const uint32_t bar_stage_free = bar_stage_full + 8 * NS;
     const uint32_t bar_acc_full = bar_stage_free + 8 * NS; // + 8 * accumulator
     const uint32_t bar_acc_drained = bar_acc_full + 16;
+    const uint32_t bar_left_full = bar_acc_drained + 16; // + 8 * buffer
+    const uint32_t bar_packed_full = bar_left_full + 8 * NA; // + 8 * packed stage
+    const uint32_t bar_packed_free = bar_packed_full + 8 * NP;
+    const uint32_t s_packed = s_b + NS * KA * ATOM_BYTES; // + packed stage * PACKED_BYTES
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
@@ -349,6 +400,12 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
             mbar_init(bar_acc_full + 8 * a, 1);
             mbar_init(bar_acc_drained + 8 * a, TM);
         }
+        for (int b = 0; b < NA; ++b)
+            mbar_init(bar_left_full + 8 * b, TM);
+        for (int s = 0; s < NP; ++s) {
+            mbar_init(bar_packed_full + 8 * s, 1);
+            mbar_init(bar_packed_free + 8 * s, TN);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -356,129 +413,189 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    const int i = mt * TM + (tid & (TM - 1)); // this epilogue thread's pixel = its TMEM lane
-    uint4 cur[KA];
-    int pa = 0; // popcount of this thread's own (left) descriptor
-    if (tid < TM) {
-        load_pixel<K>(rows_of_d + (size_t)min(i, cols - 1) * K, cur);
-        expand_pixel<K, false>(cur, s_a, tid);
-        fence_async_smem();
-#pragma unroll
-        for (int q = 0; q < KA; ++q)
-            pa += __popc(cur[q].x) + __popc(cur[q].y) + __popc(cur[q].z) + __popc(cur[q].w);
-    } else if (tid < TM + TN) {
-        load_pixel<K>(cols_of_d + (size_t)min(tid - TM, cols - 1) * K, cur); // first right tile, in flight across the barrier
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
 
+    Item it;
+    it.decode(item0, p.rows, p.mtiles);
+
     if (warp == 8) {
         // ---- MMA issuer: one thread ----
         if (tid == 8 * 32) {
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % NS, n = t / NS, a = t & 1;
-                mbar_wait(bar_stage_full + 8 * s, n & 1);
-                if (t >= 2)
-                    mbar_wait(bar_acc_drained + 8 * a, ((t - 2) >> 1) & 1); // the epilogue has read this accumulator
-                tc_fence_after();
-                const uint32_t sb = s_b + (uint32_t)(s * KA * ATOM_BYTES);
+            int g = 0; // tiles issued by this CTA
+            for (int n = 0; n < nitems; ++n) {
+                const int b = n % NA;
+                mbar_wait(bar_left_full + 8 * b, (n / NA) & 1);
+                const uint32_t sa = s_a + (uint32_t)(b * KA * ATOM_BYTES);
+                for (int t = 0; t < ntiles; ++t, ++g) {
+                    const int s = g % NS, a = g & 1;
+                    mbar_wait(bar_stage_full + 8 * s, (g / NS) & 1);
+                    if (g >= 2)
+                        mbar_wait(bar_acc_drained + 8 * a, ((g - 2) >> 1) & 1); // the epilogue has read this accumulator
+                    tc_fence_after();
+                    const uint32_t sb = s_b + (uint32_t)(s * KA * ATOM_BYTES);
 #pragma unroll
-                for (int q = 0; q < KA; ++q)
+                    for (int q = 0; q < KA; ++q)
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        tc_mma_i8(
-                            tmem + (uint32_t)(a * TN),
-                            smem_desc(s_a + q * ATOM_BYTES + kk * 32),
-                            smem_desc(sb + q * ATOM_BYTES + kk * 32),
-                            IDESC,
-                            (q | kk) != 0
-                        );
-                tc_commit(bar_stage_free + 8 * s);
-                tc_commit(bar_acc_full + 8 * a);
+                        for (int kk = 0; kk < 4; ++kk)
+                            tc_mma_i8(
+                                tmem + (uint32_t)(a * TN),
+                                smem_desc(sa + q * ATOM_BYTES + kk * 32),
+                                smem_desc(sb + q * ATOM_BYTES + kk * 32),
+                                IDESC,
+                                (q | kk) != 0
+                            );
+                    tc_commit(bar_stage_free + 8 * s);
+                    tc_commit(bar_acc_full + 8 * a);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ---- loader: one thread streams the packed descriptors of the other image's rows, tile by tile
+        //      and across item boundaries, into a small ring with TMA bulk copies ----
+        if (tid == 9 * 32) {
+            int f = 0;
+            for (int n = 0; n < nitems; ++n) {
+                const uint32_t* const row = (it.dir ? p.left : p.right) + (size_t)it.row * p.pitch_words;
+                for (int t = 0; t < ntiles; ++t, ++f) {
+                    const int s = f % NP;
+                    if (f >= NP)
+                        mbar_wait(bar_packed_free + 8 * s, (f / NP - 1) & 1);
+                    const uint32_t bytes = (uint32_t)min(TN, cols - t * TN) * K * 4;
+                    mbar_expect_tx(bar_packed_full + 8 * s, bytes);
+                    bulk_copy_g2s(s_packed + (uint32_t)(s * PACKED_BYTES), row + (size_t)t * TN * K, bytes, bar_packed_full + 8 * s);
+                }
+                it.next(p.rows, p.mtiles);
             }
         }
     } else if (warp >= 4) {
-        // ---- producers: packed right descriptors -> int8 tiles in shared memory, one tile ahead in registers ----
+        // ---- producers: one packed descriptor per thread -> a row of the uint8 tile in shared memory.
+        //      No global loads here: the fence that publishes the tile to the tensor cores waits for
+        //      every outstanding load of its thread, which would expose an L2 round trip per tile. ----
         const int r = tid - TM;
-        for (int t = 0; t < ntiles; ++t) {
-            const int s = t % NS, n = t / NS;
-            uint4 nxt[KA];
-            if (t + 1 < ntiles)
-                load_pixel<K>(cols_of_d + (size_t)min((t + 1) * TN + r, cols - 1) * K, nxt);
-            if (t >= NS)
-                mbar_wait(bar_stage_free + 8 * s, (n - 1) & 1); // the MMAs that read this stage are done
-            expand_pixel<K, true>(cur, s_b + (uint32_t)(s * KA * ATOM_BYTES), r);
+        const int total = nitems * ntiles;
+        int t = 0;
+        for (int g = 0; g < total; ++g) {
+            const int ps = g % NP, s = g % NS;
+            const int valid = min(TN, cols - t * TN); // the last tile of a row may be short: repeat its last pixel
+            mbar_wait(bar_packed_full + 8 * ps, (g / NP) & 1);
+            uint4 d[KA];
+            const uint32_t src = s_packed + (uint32_t)(ps * PACKED_BYTES) + (uint32_t)min(r, valid - 1) * (K * 4);
+#pragma unroll
+            for (int q = 0; q < KA; ++q)
+                d[q] = ld_shared_v4(src + 16 * q);
+            if (g >= NS)
+                mbar_wait(bar_stage_free + 8 * s, (g / NS - 1) & 1); // the MMAs that read this stage are done
+            expand_pixel<K, true>(d, s_b + (uint32_t)(s * KA * ATOM_BYTES), r);
+            // only now: the stores above consumed the loaded registers, so the packed slot has been read
+            // (an arrive right after the loads was observed to let the next bulk copy overtake them)
+            mbar_arrive(bar_packed_free + 8 * ps);
             fence_async_smem();
             mbar_arrive(bar_stage_full + 8 * s);
-            if (t + 1 < ntiles) {
-#pragma unroll
-                for (int q = 0; q < KA; ++q)
-                    cur[q] = nxt[q];
-            }
+            if (++t == ntiles)
+                t = 0;
         }
     } else {
         // ---- epilogue: running minima of 8192 * (ham - popc) + column over the row ----
-        int m_first = INT_MAX, m_last = INT_MAX;
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        for (int t = 0; t < ntiles; ++t) {
-            const int a = t & 1;
-            mbar_wait(bar_acc_full + 8 * a, (t >> 1) & 1);
-            tc_fence_after();
-            const uint32_t acc = lane_base + (uint32_t)(a * TN);
-            const int tile0 = t * TN;
-            int va[32], vb[32];
-            if (tile0 + TN > cols) {
-                // ragged last tile
-                TileMin32 m;
-#pragma unroll 1
-                for (int u0 = 0; u0 < TN && tile0 + u0 < cols; u0 += 32) {
-                    tc_load32_issue(acc + (uint32_t)u0, va);
-                    tc_load32_wait(va);
-                    fold32_guarded<NODUPES>(va, u0, cols - tile0, m);
-                }
-                tc_fence_before();
-                mbar_arrive(bar_acc_drained + 8 * a);
-                merge_tile<NODUPES>(m, tile0, m_first, m_last);
-            } else if constexpr (K == 4) {
-                // 16-bit lanes: the second 64 columns are in flight while the first are folded
-                TileMin16 m;
-                tc_load64_packed_issue(acc, va);
-                tc_load32_wait(va);
-                tc_load64_packed_issue(acc + 64, vb);
-                fold64_packed<NODUPES, 0>(va, m);
-                tc_load32_wait(vb);
-                tc_fence_before();
-                mbar_arrive(bar_acc_drained + 8 * a); // the accumulator is in registers: hand it back before the last fold
-                fold64_packed<NODUPES, 64>(vb, m);
-                merge_tile<NODUPES>(m, tile0, m_first, m_last);
-            } else {
-                TileMin32 m;
-                tc_load32_issue(acc, va);
-                tc_load32_wait(va);
-                tc_load32_issue(acc + 32, vb);
-                fold32<NODUPES, 0>(va, m);
-                tc_load32_wait(vb);
-                tc_load32_issue(acc + 64, va);
-                fold32<NODUPES, 32>(vb, m);
-                tc_load32_wait(va);
-                tc_load32_issue(acc + 96, vb);
-                fold32<NODUPES, 64>(va, m);
-                tc_load32_wait(vb);
-                tc_fence_before();
-                mbar_arrive(bar_acc_drained + 8 * a);
-                fold32<NODUPES, 96>(vb, m);
-                merge_tile<NODUPES>(m, tile0, m_first, m_last);
-            }
+        int pa_next = 0;
+        // this thread's pixel of item `at` -> row `tid` of left buffer `b`; returns its popcount
+        auto load_left = [&](const Item& at, uint4(&d)[KA]) {
+            const uint32_t* const row = (at.dir ? p.right : p.left) + (size_t)at.row * p.pitch_words;
+            load_pixel<K>(row + (size_t)min(at.mt * TM + tid, cols - 1) * K, d);
+        };
+        auto stage_left = [&](const uint4(&d)[KA], int n) {
+            const int b = n % NA;
+            expand_pixel<K, false>(d, s_a + (uint32_t)(b * KA * ATOM_BYTES), tid);
+            fence_async_smem();
+            mbar_arrive(bar_left_full + 8 * b);
+            int pc = 0;
+#pragma unroll
+            for (int q = 0; q < KA; ++q)
+                pc += __popc(d[q].x) + __popc(d[q].y) + __popc(d[q].z) + __popc(d[q].w);
+            return pc;
+        };
+        uint4 dl[KA];
+        if (nitems > 0) {
+            load_left(it, dl);
+            pa_next = stage_left(dl, 0);
         }
-        if (i < cols) {
-            const size_t at = (size_t)row * cols + i;
-            // m = 8192 * (cost - popc) + column: arithmetic shift = floor, the low bits are the column
-            (dir ? p.rev_first : p.fwd_first)[at] = ((uint32_t)(pa + (m_first >> COL_BITS)) << 16) | ((uint32_t)m_first & COL_MAX);
-            if constexpr (NODUPES)
-                (dir ? p.rev_last : p.fwd_last)[at] =
-                    ((uint32_t)(pa + (m_last >> COL_BITS)) << 16) | ((65535u - COL_MAX) + ((uint32_t)m_last & COL_MAX));
+        int g = 0;
+        for (int n = 0; n < nitems; ++n) {
+            const int pa = pa_next; // popcount of this thread's own descriptor
+            Item nx = it;
+            nx.next(p.rows, p.mtiles);
+            int m_first = INT_MAX, m_last = INT_MAX;
+            if (n + 1 < nitems)
+                load_left(nx, dl); // in flight over the first tiles of this item
+            for (int t = 0; t < ntiles; ++t, ++g) {
+                const int a = g & 1;
+                mbar_wait(bar_acc_full + 8 * a, (g >> 1) & 1);
+                tc_fence_after();
+                const uint32_t acc = lane_base + (uint32_t)(a * TN);
+                const int tile0 = t * TN;
+                int va[32], vb[32];
+                if (tile0 + TN > cols) {
+                    // ragged last tile
+                    TileMin32 m;
+#pragma unroll 1
+                    for (int u0 = 0; u0 < TN && tile0 + u0 < cols; u0 += 32) {
+                        tc_load32_issue(acc + (uint32_t)u0, va);
+                        tc_load32_wait(va);
+                        fold32_guarded<NODUPES>(va, u0, cols - tile0, m);
+                    }
+                    tc_fence_before();
+                    mbar_arrive(bar_acc_drained + 8 * a);
+                    merge_tile<NODUPES>(m, tile0, m_first, m_last);
+                } else if constexpr (K == 4) {
+                    // 16-bit lanes: the second 64 columns are in flight while the first are folded
+                    TileMin16 m;
+                    tc_load64_packed_issue(acc, va);
+                    tc_load32_wait(va);
+                    tc_load64_packed_issue(acc + 64, vb);
+                    fold64_packed<NODUPES, 0>(va, m);
+                    tc_load32_wait(vb);
+                    tc_fence_before();
+                    mbar_arrive(bar_acc_drained + 8 * a); // the accumulator is in registers: hand it back before the last fold
+                    fold64_packed<NODUPES, 64>(vb, m);
+                    merge_tile<NODUPES>(m, tile0, m_first, m_last);
+                } else {
+                    TileMin32 m;
+                    tc_load32_issue(acc, va);
+                    tc_load32_wait(va);
+                    tc_load32_issue(acc + 32, vb);
+                    fold32<NODUPES, 0>(va, m);
+                    tc_load32_wait(vb);
+                    tc_load32_issue(acc + 64, va);
+                    fold32<NODUPES, 32>(vb, m);
+                    tc_load32_wait(va);
+                    tc_load32_issue(acc + 96, vb);
+                    fold32<NODUPES, 64>(va, m);
+                    tc_load32_wait(vb);
+                    tc_fence_before();
+                    mbar_arrive(bar_acc_drained + 8 * a);
+                    fold32<NODUPES, 96>(vb, m);
+                    merge_tile<NODUPES>(m, tile0, m_first, m_last);
+                }
+                // The next item's left tile. With two buffers: early, the other buffer was last read by the
+                // previous item, whose MMAs are all complete. With one: once this item's last MMAs are
+                // complete, which the wait on its last accumulator has established. Its descriptor was requested at
+                // the start of the item.
+                if (n + 1 < nitems && t == (NA == 2 ? min(2, ntiles - 1) : ntiles - 1))
+                    pa_next = stage_left(dl, n + 1);
+            }
+            const int i = it.mt * TM + tid;
+            if (i < cols) {
+                const size_t at = (size_t)it.row * cols + i;
+                // m = 8192 * (cost - popc) + column: arithmetic shift = floor, the low bits are the column
+                (it.dir ? p.rev_first : p.fwd_first)[at] = ((uint32_t)(pa + (m_first >> COL_BITS)) << 16) | ((uint32_t)m_first & COL_MAX);
+                if constexpr (NODUPES)
+                    (it.dir ? p.rev_last : p.fwd_last)[at] =
+                        ((uint32_t)(pa + (m_last >> COL_BITS)) << 16) | ((65535u - COL_MAX) + ((uint32_t)m_last & COL_MAX));
+            }
+            it = nx;
         }
     }
 
@@ -491,16 +608,32 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
 }
 
 template<int K, bool NODUPES>
-cudaError_t launch_k(const MmaArgs& p, int rows, int dirs, cudaStream_t stream) {
+cudaError_t launch_k(MmaArgs p, int dirs, cudaStream_t stream) {
     const int smem = search_mma_smem_bytes(K);
     auto kernel = search_mma_kernel<K, NODUPES>;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess)
         return err;
-    const long long grid = (long long)rows * p.mtiles;
-    if (grid <= 0 || grid > 0x7FFFFFFFLL)
+    // persistent CTAs: as many as are resident at once (__launch_bounds__ and the shared-memory budget
+    // of search_mma_smem_bytes are laid out for 2 per SM up to 256 bits, 1 beyond; the occupancy API
+    // reports 1 for the 2-CTA variants until the carve-out is raised, so it is not asked), each walking a
+    // contiguous share of the items
+    static thread_local int resident = 0; // per template instance
+    if (resident == 0) {
+        int dev = 0, sms = 0;
+        if ((err = cudaGetDevice(&dev)) != cudaSuccess)
+            return err;
+        if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
+            return err;
+        if ((err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
+            return err;
+        resident = sms * (K <= 8 ? 2 : 1);
+    }
+    p.items = (long long)dirs * p.rows * p.mtiles;
+    if (p.items > 0x7FFFFFFFLL)
         return cudaErrorInvalidConfiguration;
-    kernel<<<dim3((unsigned)grid, (unsigned)dirs), NTHREADS, smem, stream>>>(p);
+    const unsigned grid = (unsigned)(p.items < resident ? p.items : resident);
+    kernel<<<grid, NTHREADS, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -508,7 +641,9 @@ cudaError_t launch_k(const MmaArgs& p, int rows, int dirs, cudaStream_t stream) 
 
 int search_mma_smem_bytes(int K) {
     const int stages = K == 4 ? STAGES<4> : K == 8 ? STAGES<8> : K == 12 ? STAGES<12> : STAGES<16>;
-    return (1 + stages) * (K / 4) * ATOM_BYTES + 1024; // left tile + right stages + alignment slack
+    const int lefts = K == 4 ? LEFT_BUFFERS<4> : 1;
+    const int packed = K == 4 ? PACKED_STAGES<4> : K == 8 ? PACKED_STAGES<8> : PACKED_STAGES<16>;
+    return (lefts + stages) * (K / 4) * ATOM_BYTES + packed * TN * K * 4 + 1024; // left tiles, right stages, packed ring, alignment slack
 }
 
 bool search_mma_supports(int K, int cols) {
@@ -534,6 +669,7 @@ cudaError_t launch_search_mma(
     MmaArgs p;
     p.left = desc0;
     p.right = desc1;
+    p.rows = rows;
     p.cols = cols;
     p.pitch_words = desc_pitch_words;
     p.mtiles = (cols + TM - 1) / TM;
@@ -546,13 +682,13 @@ cudaError_t launch_search_mma(
     const bool nodupes = (flags & FLAG_NODUPES) != 0;
     switch (K) {
         case 4:
-            return nodupes ? launch_k<4, true>(p, rows, dirs, stream) : launch_k<4, false>(p, rows, dirs, stream);
+            return nodupes ? launch_k<4, true>(p, dirs, stream) : launch_k<4, false>(p, dirs, stream);
         case 8:
-            return nodupes ? launch_k<8, true>(p, rows, dirs, stream) : launch_k<8, false>(p, rows, dirs, stream);
+            return nodupes ? launch_k<8, true>(p, dirs, stream) : launch_k<8, false>(p, dirs, stream);
         case 12:
-            return nodupes ? launch_k<12, true>(p, rows, dirs, stream) : launch_k<12, false>(p, rows, dirs, stream);
+            return nodupes ? launch_k<12, true>(p, dirs, stream) : launch_k<12, false>(p, dirs, stream);
         case 16:
-            return nodupes ? launch_k<16, true>(p, rows, dirs, stream) : launch_k<16, false>(p, rows, dirs, stream);
+            return nodupes ? launch_k<16, true>(p, dirs, stream) : launch_k<16, false>(p, dirs, stream);
     }
     return cudaErrorInvalidValue;
 }
