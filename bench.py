@@ -11,7 +11,9 @@ GPU (frame-sharded across GPUs, weak scaling, no data-path collective: frames ar
   e2e        same metric through the host-buffer C-ABI entry point (bicos_b200_match_host, what
              pybicos' BICOS_Match calls): pinned host stacks in, host disparity + corrmap out,
              copies inside the timed region
-  roofline   the dominant kernel (row-wise Hamming search): algorithmic popc32/s against the
+  roofline   the dominant kernel (row-wise Hamming search). Tensor-core engine (default): int8 TOP/s
+             against the dense int8 rate measured live with cuBLASLt; the popcount engine is timed on the
+             same frames and reported as roofline.other_engine: algorithmic popc32/s against the
              measured pure-POPC issue rate of this GPU; the two HBM-bound kernels are listed
              under roofline_other against MEASURED_PEAKS.json
   cpu_baseline  the unmodified reference CPU backend (oracle/_ref) on a bounded row sample
@@ -127,6 +129,33 @@ def measure_popc_peak(sm_max_mhz):
         except Exception:
             pass
     return 16.0 * 148 * sm_max_mhz * 1e6, "nominal 16 POPC/clk/SM x 148 SM x max clock"
+
+
+def measure_int8_peak():
+    """Dense int8 tensor-core rate of this GPU: cuBLASLt through torch._int_mm, 8192^3, best of 10 (TOP/s)."""
+    import torch
+
+    try:
+        a = torch.randint(-8, 8, (8192, 8192), dtype=torch.int8, device="cuda")
+        b = torch.randint(-8, 8, (8192, 8192), dtype=torch.int8, device="cuda").t().contiguous().t()
+        torch._int_mm(a, b)
+        best = float("inf")
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch._int_mm(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2 * 8192**3 / (best * 1e-3) / 1e12, "measured live (torch._int_mm 8192^3 = cuBLASLt int8, best of 10, CUDA events)"
+    except Exception as e:  # noqa: BLE001
+        bf16 = 1632.7
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                bf16 = float(json.load(f)["bf16_tflops"])
+        except (OSError, KeyError, ValueError):
+            pass
+        return 2 * bf16, f"2 x the measured dense bf16 rate of MEASURED_PEAKS.json (torch._int_mm failed: {type(e).__name__})"
 
 
 def cpu_reference_run(rows, threads=None):
@@ -316,17 +345,48 @@ def main():
             traffic = json.load(f)
     except OSError:
         pass
-    popc_issued = COLS * px * 3  # the kernel's carry-save form: 3 POPC per 128-bit pair
-    roofline = {
-        "kernel": "search_kernel<4, CONSISTENCY>", "bound": "popc", "achieved": popc_alg / t_se / 1e12,
-        "peak": popc_peak / 1e12, "unit": "Tpopc32/s", "frac": popc_alg / t_se / popc_peak,
-        "pipe_frac": popc_issued / t_se / popc_peak, "traffic": traffic.get("search"),
-        "hbm_frac": (traffic.get("search", 0) / t_se / 1e9 / hbm_peak) if traffic.get("search") else None,
-        "peak_source": popc_src, "ms_per_launch": t_se * 1e3,
-        "note": "frac = algorithmic popc32 (SURVEY 8d: 4 words per 128-bit pair) over the measured POPC issue rate; the "
-                "kernel issues 3 POPC per pair after carry-save compression, so frac exceeds 1 while pipe_frac (issued "
-                "POPC over the same peak; ncu: XU pipe 95.5 % active) is the share of POPC-pipe cycles in use",
+    # the other engine on the same frames, for the record (stage timer of the handle)
+    engine = lb.search_engine()
+    tensor = engine != "popc"  # K = 4, 2048 columns: inside the tensor-core engine's range
+    lb.set_search_engine("popc" if tensor else "tensor")
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    h.set_profiling(True)
+    for _ in range(3):
+        step()
+    other_ms, other_n = h.stage_times()
+    h.set_profiling(False)
+    lb.set_search_engine(engine)
+    t_other = 1e-3 * other_ms[1] / max(other_n, 1)
+    t_popc, t_mma = (t_other, t_se) if tensor else (t_se, t_other)
+
+    popc_issued = COLS * px * 3  # the popc kernel's carry-save form: 3 POPC per 128-bit pair
+    popc_line = {
+        "kernel": "search_kernel<4, CONSISTENCY>", "bound": "popc", "achieved": popc_alg / t_popc / 1e12,
+        "peak": popc_peak / 1e12, "unit": "Tpopc32/s", "frac": popc_alg / t_popc / popc_peak,
+        "pipe_frac": popc_issued / t_popc / popc_peak, "traffic": traffic.get("search"),
+        "peak_source": popc_src, "ms_per_launch": t_popc * 1e3,
+        "note": "the integer-pipe engine (BICOS_B200_SEARCH_ENGINE=popc): frac = algorithmic popc32 (SURVEY 8d) over the "
+                "measured POPC issue rate; 3 POPC are issued per 128-bit pair, pipe_frac is the share of the POPC pipe in use",
     }
+    int8_peak, int8_src = measure_int8_peak()
+    dirs = 2  # Consistency: forward and reverse search, each a full W x W x 128 product per row
+    mma_ops = 2.0 * COLS * px * 32 * K * dirs
+    smem_bytes = (COLS / 128) * (px / 128) * dirs * 52 * 1024  # per 128x128 tile: 32 KB operand reads, 16 KB expansion, 4 KB packed ring
+    mma_line = {
+        "kernel": "search_mma_kernel<4, CONSISTENCY>", "bound": "tensor", "achieved": mma_ops / t_mma / 1e12,
+        "peak": int8_peak, "unit": "TOP/s", "frac": mma_ops / t_mma / 1e12 / int8_peak, "traffic": traffic.get("search_mma"),
+        "peak_source": int8_src, "ms_per_launch": t_mma * 1e3,
+        "smem_frac": smem_bytes / t_mma / (128.0 * 148 * sm_max * 1e6),
+        "note": "the tensor-core engine (default): W x W x 128-bit Hamming matrix per row and direction as int8 tcgen05.mma "
+                "(kind::i8, TMEM accumulators), argmin in the epilogue; achieved = 2*W*P*bits*directions int8 ops per "
+                "launch over the stage time. smem_frac: shared-memory bytes the kernel moves (operand reads of the MMAs + "
+                "operand expansion) over 128 B/clk/SM - the resource ncu shows closest to its limit",
+    }
+    roofline = mma_line if tensor else popc_line
+    roofline["engine"] = "tensor" if tensor else "popc"
+    roofline["other_engine"] = popc_line if tensor else mma_line
     roofline_other = [
         {"kernel": "transform_limited_kernel<u8,4> x2", "bound": "hbm", "achieved": tr_bytes / t_tr / 1e9,
          "peak": hbm_peak, "unit": "GB/s", "frac": tr_bytes / t_tr / 1e9 / hbm_peak, "traffic": traffic.get("transform"),

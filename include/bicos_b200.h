@@ -195,6 +195,17 @@ int bicos_b200_stage_times(bicos_b200_handle h, double* ms_out3, long long* matc
 /* How many kernels of this library have been launched through the handle (bench bookkeeping). */
 long long bicos_b200_kernel_launches(bicos_b200_handle h);
 
+/* The search stage has two engines with identical results: BICOS_B200_SEARCH_TENSOR computes the
+ * row's Hamming matrix as an int8 GEMM on the tensor cores (tcgen05, accumulators in TMEM, argmin as
+ * epilogue; descriptors of 4/8/12/16 words, rows of up to 8192 pixels), BICOS_B200_SEARCH_POPC is the
+ * XOR + POPC kernel on the integer pipes (any descriptor, rows of up to 32767 pixels). AUTO (the
+ * default, also settable as environment BICOS_B200_SEARCH_ENGINE = auto | popc | mma) takes the
+ * tensor-core engine wherever it applies. Process-wide; forcing TENSOR makes unsupported shapes
+ * fail with BICOS_B200_ERR_CUDA instead of falling back. */
+enum { BICOS_B200_SEARCH_AUTO = 0, BICOS_B200_SEARCH_POPC = 1, BICOS_B200_SEARCH_TENSOR = 2 };
+int bicos_b200_set_search_engine(int engine);
+int bicos_b200_get_search_engine(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,9 @@ EXPORTS = (
     "bicos_b200_match_host", "bicos_b200_match_host_begin", "bicos_b200_match_host_end", "bicos_b200_match_rows", "bicos_b200_synchronize",
     "bicos_b200_kernel_launches", "bicos_b200_set_profiling", "bicos_b200_stage_times",
     "bicos_b200_shared_alloc", "bicos_b200_shared_open", "bicos_b200_shared_close", "bicos_b200_shared_free",
+    "bicos_b200_set_search_engine", "bicos_b200_get_search_engine",
 )
+SEARCH_ENGINES = {"auto": 0, "popc": 1, "tensor": 2}
 IPC_HANDLE_BYTES = 64
 
 
@@ -95,6 +97,8 @@ def lib():
                 "(or __graft_entry__.build()); there is no CPU or PyTorch fallback")
         L = ctypes.CDLL(LIB_PATH)
         L.bicos_b200_last_error.restype = ctypes.c_char_p
+        L.bicos_b200_set_search_engine.argtypes = [ctypes.c_int]
+        L.bicos_b200_get_search_engine.argtypes = []
         L.bicos_b200_kernel_launches.restype = ctypes.c_longlong
         L.bicos_b200_kernel_launches.argtypes = [ctypes.c_void_p]
         vp, i, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
@@ -136,6 +140,16 @@ MODE_WIDE = 2  # BICOS_B200_MODE_WIDE
 def descriptor_words(n: int, mode_full: bool = False, wide: bool = False) -> int:
     """Words per descriptor: 1/2/4/8 as the reference dispatches them; `wide` (extension) adds 12 / 16."""
     return _check(lib().bicos_b200_descriptor_words(n, int(mode_full) | (MODE_WIDE if wide else 0)))
+
+
+def set_search_engine(engine: str) -> None:
+    """'auto' (tensor cores where they apply), 'popc' or 'tensor': bicos_b200_set_search_engine, process-wide."""
+    _check(lib().bicos_b200_set_search_engine(SEARCH_ENGINES[engine]))
+
+
+def search_engine() -> str:
+    code = lib().bicos_b200_get_search_engine()
+    return next(k for k, v in SEARCH_ENGINES.items() if v == code)
 
 
 def _ptr_array(ptrs: Sequence[int]):

@@ -1040,4 +1040,15 @@ long long bicos_b200_kernel_launches(bicos_b200_handle h) {
     return h ? h->launches : 0;
 }
 
+int bicos_b200_set_search_engine(int engine) {
+    if (engine < BICOS_B200_SEARCH_AUTO || engine > BICOS_B200_SEARCH_TENSOR)
+        return fail(BICOS_B200_ERR_INVALID, "search engine %d (0 = auto, 1 = popc, 2 = tensor)", engine);
+    set_search_engine(engine);
+    return 0;
+}
+
+int bicos_b200_get_search_engine(void) {
+    return search_engine();
+}
+
 } // extern "C"

@@ -540,7 +540,7 @@ int search_engine() {
     int e = g_engine.load(std::memory_order_relaxed);
     if (e < 0) {
         const char* v = getenv("BICOS_B200_SEARCH_ENGINE");
-        e = !v ? 1 : !strcmp(v, "auto") ? 0 : !strcmp(v, "mma") ? 2 : 1; // default popc until the tensor-core engine is validated on the device
+        e = !v ? 0 : !strcmp(v, "popc") ? 1 : !strcmp(v, "mma") ? 2 : 0;
         g_engine.store(e, std::memory_order_relaxed);
     }
     return e;

@@ -245,10 +245,10 @@ struct TileMin32 {
 };
 
 struct TileMin16 {
-    uint32_t f[4], l[4];
+    uint32_t f[8], l[8]; // eight chains: the epilogue warps are few, so the fold must not wait on itself
     __device__ __forceinline__ TileMin16() {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 8; ++c)
             f[c] = l[c] = 0x7FFF7FFFu;
     }
 };
@@ -285,9 +285,9 @@ __device__ __forceinline__ void fold64_packed(const int (&v)[32], TileMin16& m) 
         constexpr uint32_t ONE = 0x00010001u;
         const uint32_t uf = (uint32_t)(U0 + 2 * r) * ONE + 0x00010000u; // columns U0 + 2r | U0 + 2r + 1
         const uint32_t ul = (uint32_t)(127 - U0 - 2 * r) * ONE - 0x00010000u; // 127 - column
-        m.f[r & 3] = __viaddmin_s16x2((uint32_t)v[r], uf, m.f[r & 3]);
+        m.f[r & 7] = __viaddmin_s16x2((uint32_t)v[r], uf, m.f[r & 7]);
         if constexpr (NODUPES)
-            m.l[r & 3] = __viaddmin_s16x2((uint32_t)v[r], ul, m.l[r & 3]);
+            m.l[r & 7] = __viaddmin_s16x2((uint32_t)v[r], ul, m.l[r & 7]);
     }
 }
 
@@ -303,16 +303,16 @@ __device__ __forceinline__ void merge_tile(const TileMin32& m, int tile0, int& m
         m_last = min(m_last, widen_key(min(min(m.l[0], m.l[1]), min(m.l[2], m.l[3]))) + (COL_MAX - 127 - tile0));
 }
 
-__device__ __forceinline__ int min_of_lanes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    const uint32_t m = __vmins2(__vmins2(a, b), __vmins2(c, d));
+__device__ __forceinline__ int min_of_lanes(const uint32_t (&c)[8]) {
+    const uint32_t m = __vmins2(__vmins2(__vmins2(c[0], c[1]), __vmins2(c[2], c[3])), __vmins2(__vmins2(c[4], c[5]), __vmins2(c[6], c[7])));
     return min((int)(short)(m & 0xFFFFu), (int)(short)(m >> 16));
 }
 
 template<bool NODUPES>
 __device__ __forceinline__ void merge_tile(const TileMin16& m, int tile0, int& m_first, int& m_last) {
-    m_first = min(m_first, widen_key(min_of_lanes(m.f[0], m.f[1], m.f[2], m.f[3])) + tile0);
+    m_first = min(m_first, widen_key(min_of_lanes(m.f)) + tile0);
     if constexpr (NODUPES)
-        m_last = min(m_last, widen_key(min_of_lanes(m.l[0], m.l[1], m.l[2], m.l[3])) + (COL_MAX - 127 - tile0));
+        m_last = min(m_last, widen_key(min_of_lanes(m.l)) + (COL_MAX - 127 - tile0));
 }
 
 struct MmaArgs {
@@ -550,15 +550,16 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
                     mbar_arrive(bar_acc_drained + 8 * a);
                     merge_tile<NODUPES>(m, tile0, m_first, m_last);
                 } else if constexpr (K == 4) {
-                    // 16-bit lanes: the second 64 columns are in flight while the first are folded
+                    // 16-bit lanes: the whole accumulator goes to 64 registers and is handed back before the
+                    // fold, so that the next MMAs into it overlap the fold
                     TileMin16 m;
                     tc_load64_packed_issue(acc, va);
-                    tc_load32_wait(va);
                     tc_load64_packed_issue(acc + 64, vb);
-                    fold64_packed<NODUPES, 0>(va, m);
+                    tc_load32_wait(va);
                     tc_load32_wait(vb);
                     tc_fence_before();
-                    mbar_arrive(bar_acc_drained + 8 * a); // the accumulator is in registers: hand it back before the last fold
+                    mbar_arrive(bar_acc_drained + 8 * a);
+                    fold64_packed<NODUPES, 0>(va, m);
                     fold64_packed<NODUPES, 64>(vb, m);
                     merge_tile<NODUPES>(m, tile0, m_first, m_last);
                 } else {

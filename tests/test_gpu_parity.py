@@ -9,9 +9,19 @@ require) exact equality.
 import numpy as np
 import pytest
 
+import libbicos_b200 as lb
 from libbicos_b200 import Config, synth
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["auto", "popc"])
+def engine(request):
+    """Both search engines: 'auto' = tensor cores (tcgen05) wherever they apply, 'popc' = the integer-pipe kernel."""
+    lb.set_search_engine(request.param)
+    yield request.param
+    lb.set_search_engine("auto")
+
 
 FLAG_NODUPES, FLAG_CONSISTENCY = 1, 2
 
@@ -86,7 +96,7 @@ def _random_desc(rng, rows, cols, k, bits):
 @pytest.mark.parametrize("k", [1, 2, 4, 8, 12, 16])
 @pytest.mark.parametrize("flags", [FLAG_NODUPES, FLAG_CONSISTENCY, FLAG_NODUPES | FLAG_CONSISTENCY])
 @pytest.mark.parametrize("cols,bits", [(97, 3), (512, 8), (700, 32), (1300, 5)])
-def test_search_postfilter_bit_exact(handle, oracles, k, flags, cols, bits):
+def test_search_postfilter_bit_exact(handle, oracles, engine, k, flags, cols, bits):
     import torch
 
     rng = np.random.default_rng(k * 100 + flags * 10 + cols)
@@ -241,8 +251,9 @@ def test_tiny_and_ragged_images(handle, oracles, rows, cols):
 
 
 @pytest.mark.parametrize("k,cols,flags", [(8, 4100, 3), (4, 4100, 2), (1, 9000, 1), (2, 2050, 3)])
-def test_search_wide_rows_split_units(handle, oracles, k, cols, flags):
-    """Wide rows: several chunks per unit and up to 8 CTAs per unit merged by atomicMin."""
+def test_search_wide_rows_split_units(handle, oracles, engine, k, cols, flags):
+    """Wide rows: several chunks per unit and up to 8 CTAs per unit merged by atomicMin (popc); 33 column tiles
+    per item (tensor). 9000 columns are beyond the tensor-core engine: auto falls back to popc."""
     import torch
 
     rng = np.random.default_rng(k * 7 + cols)
@@ -265,6 +276,63 @@ def test_search_wide_rows_split_units(handle, oracles, k, cols, flags):
     cfg = Config(nxcorr_threshold=None, consistency=bool(flags & FLAG_CONSISTENCY), max_lr_diff=2, no_dupes=flags == 3)
     disp, _, _ = handle.refine(dummy, dummy, cfg, keys)
     assert np.array_equal(disp.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("k,rows,cols,flags", [(4, 700, 384, 3), (4, 40, 2048, 2), (8, 500, 300, 1), (8, 12, 2448, 3),
+                                               (12, 330, 256, 2), (16, 310, 200, 3), (4, 1300, 130, 0)])
+def test_search_engines_identical(handle, k, rows, cols, flags):
+    """The tensor-core engine (int8 GEMM + argmin epilogue) reproduces the popcount engine's four key arrays bit
+    for bit, at sizes where a persistent CTA walks several work items (rows x M tiles x directions > resident CTAs)
+    and with descriptors drawn from a small pool, so that exact ties are the rule."""
+    import torch
+
+    rng = np.random.default_rng(k + rows + cols + flags)
+    pool = rng.integers(0, 2**32, size=(48, k), dtype=np.uint64).astype(np.uint32)
+
+    def draw():
+        d = pool[rng.integers(0, len(pool), size=(rows, cols))]
+        flip = rng.integers(0, 4, size=(rows, cols, 1)) > 1
+        bit = rng.integers(0, 32 * k, size=(rows, cols))
+        mask = np.zeros((rows, cols, k), dtype=np.uint32)
+        np.put_along_axis(mask, (bit // 32)[..., None], (np.uint32(1) << (bit % 32).astype(np.uint32))[..., None], axis=2)
+        return d ^ (mask * flip)
+
+    pitch = (cols * k + 3) // 4 * 4
+
+    def pitched(d):
+        buf = np.zeros((rows, pitch), dtype=np.uint32)
+        buf[:, : cols * k] = d.reshape(rows, cols * k)
+        return torch.from_numpy(buf.view(np.int32)).cuda()
+
+    d0, d1 = pitched(draw()), pitched(draw())
+    got = {}
+    try:
+        for name in ("popc", "tensor"):
+            lb.set_search_engine(name)
+            got[name] = [None if a is None else a.cpu().numpy() for a in handle.search(d0, d1, k, cols, flags)]
+    finally:
+        lb.set_search_engine("auto")
+    for a, b, what in zip(got["popc"], got["tensor"], ("fwd_first", "fwd_last", "rev_first", "rev_last")):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert np.array_equal(a, b), f"{what}: {(a != b).sum()} of {a.size} keys differ"
+
+
+def test_tensor_engine_refuses_what_it_cannot_do(handle):
+    """Forced tensor engine: 32-bit descriptors and rows beyond 8192 pixels are errors, not silent fallbacks."""
+    import torch
+
+    try:
+        lb.set_search_engine("tensor")
+        d = torch.zeros((2, 64), dtype=torch.int32, device="cuda")
+        with pytest.raises(lb.BicosError):
+            handle.search(d, d, 1, 64, FLAG_NODUPES)
+        wide = torch.zeros((1, 9000 * 4), dtype=torch.int32, device="cuda")
+        with pytest.raises(lb.BicosError):
+            handle.search(wide, wide, 4, 9000, FLAG_NODUPES)
+    finally:
+        lb.set_search_engine("auto")
+    assert lb.search_engine() == "auto"
 
 
 def test_randomised_configurations(handle, oracles):
