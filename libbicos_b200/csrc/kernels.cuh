@@ -126,6 +126,8 @@ cudaError_t launch_search_mma(
 );
 bool search_mma_supports(int K, int cols);
 int search_mma_smem_bytes(int K);
+int search_mma_variant(); // tensor-core kernel variant, see search_mma.cu
+void set_search_mma_variant(int v);
 int search_engine(); // initial value: environment BICOS_B200_SEARCH_ENGINE = auto | popc | mma
 void set_search_engine(int engine);
 

@@ -41,6 +41,7 @@
 #include "kernels.cuh"
 
 #include <limits.h>
+#include <stdlib.h>
 
 namespace bicos_b200 {
 namespace {
@@ -105,6 +106,27 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
     return v;
 }
 
+// One lane of a converged warp. The MMA issuer runs as a whole warp with uniform control flow and uniform
+// operands and only the tcgen05 instructions themselves are elected: a `tid == first lane` branch around
+// the loop makes ptxas wrap every uniform-register operand in an ELECT / BRA.U.ANY loop, and the issuing
+// thread, not the tensor pipe, becomes the bound (ncu source page, r01).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(pred)
+    );
+    return pred != 0;
+}
+
+__device__ __forceinline__ uint32_t uniform(uint32_t v) {
+    return __shfl_sync(0xFFFFFFFFu, v, 0);
+}
+
 __device__ __forceinline__ void fence_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -159,6 +181,36 @@ __device__ __forceinline__ void tc_load64_packed_issue(uint32_t taddr, int (&v)[
 
 __device__ __forceinline__ void tc_load32_wait(int (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])::"memory");
+}
+
+// 32 consecutive 32-bit columns of this thread's lane <- registers (asynchronous; tc_store_wait before the
+// fence that publishes them)
+__device__ __forceinline__ void tc_store32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        :
+        : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory"
+    );
+}
+
+__device__ __forceinline__ void tc_store_wait() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]^T: the left operand read from tensor memory (lane = row, four int8 of K
+// per 32-bit column), so that only the streamed operand costs shared-memory bandwidth
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
+        "}"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory"
+    );
 }
 
 // Shared-memory matrix descriptor (sm_100 format): K-major rows of 128 bytes, 128-byte swizzle,
@@ -422,33 +474,37 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
     it.decode(item0, p.rows, p.mtiles);
 
     if (warp == 8) {
-        // ---- MMA issuer: one thread ----
-        if (tid == 8 * 32) {
+        // ---- MMA issuer: the whole warp walks the tiles, one elected lane issues ----
+        {
+            const uint32_t u_tmem = uniform(tmem), u_sa = uniform(s_a), u_sb = uniform(s_b);
             int g = 0; // tiles issued by this CTA
             for (int n = 0; n < nitems; ++n) {
                 const int b = n % NA;
                 mbar_wait(bar_left_full + 8 * b, (n / NA) & 1);
-                const uint32_t sa = s_a + (uint32_t)(b * KA * ATOM_BYTES);
+                const uint32_t sa = u_sa + (uint32_t)(b * KA * ATOM_BYTES);
                 for (int t = 0; t < ntiles; ++t, ++g) {
                     const int s = g % NS, a = g & 1;
                     mbar_wait(bar_stage_full + 8 * s, (g / NS) & 1);
                     if (g >= 2)
                         mbar_wait(bar_acc_drained + 8 * a, ((g - 2) >> 1) & 1); // the epilogue has read this accumulator
                     tc_fence_after();
-                    const uint32_t sb = s_b + (uint32_t)(s * KA * ATOM_BYTES);
+                    const uint32_t sb = u_sb + (uint32_t)(s * KA * ATOM_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int q = 0; q < KA; ++q)
+                        for (int q = 0; q < KA; ++q)
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            tc_mma_i8(
-                                tmem + (uint32_t)(a * TN),
-                                smem_desc(sa + q * ATOM_BYTES + kk * 32),
-                                smem_desc(sb + q * ATOM_BYTES + kk * 32),
-                                IDESC,
-                                (q | kk) != 0
-                            );
-                    tc_commit(bar_stage_free + 8 * s);
-                    tc_commit(bar_acc_full + 8 * a);
+                            for (int kk = 0; kk < 4; ++kk)
+                                tc_mma_i8(
+                                    u_tmem + (uint32_t)(a * TN),
+                                    smem_desc(sa + q * ATOM_BYTES + kk * 32),
+                                    smem_desc(sb + q * ATOM_BYTES + kk * 32),
+                                    IDESC,
+                                    (q | kk) != 0
+                                );
+                        tc_commit(bar_stage_free + 8 * s);
+                        tc_commit(bar_acc_full + 8 * a);
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -608,6 +664,323 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Variant for 128- and 256-bit descriptors: ONE CTA per SM, 256 left pixels per work item, the left
+// operand resident in tensor memory. The kernel above is bound by the shared-memory pipe (MMA operand
+// reads 32 KB + expansion stores 16 KB per 128 x 128 tile); here an MMA reads only the streamed operand
+// from shared memory (16 KB) and every expanded right tile serves two MMA groups (8 KB of stores per
+// 128 x 128 of output). TMEM: three 128-column accumulators in rotation (columns 0..383) + the left
+// operand, 2 x 32 columns per 128 descriptor bits, double-buffered for 128 bits (columns 384..511).
+//   warps 0-3 / 4-7  epilogue of the first / second 128 left pixels (the four lane quadrants each)
+//   warps 8-11       producers        warp 12  MMA issuer        warp 13  loader
+constexpr int V2_THREADS = 448;
+constexpr uint32_t V2_ACC_COLS = 3 * TN;
+template<int K>
+constexpr int V2_STAGES = K == 4 ? 8 : 4; // 128 KB of right tiles
+constexpr int V2_PACKED = 4;
+template<int K>
+constexpr int V2_LEFT_BUFFERS = K == 4 ? 2 : 1;
+
+// (1 - 2a) * 2^(7 - s) bytes of one descriptor word, the eight words s = 0..7 = TMEM columns 8 wi + s
+template<int K>
+__device__ __forceinline__ void expand_left_to_tmem(const uint4 (&d)[K / 4], uint32_t taddr) {
+#pragma unroll
+    for (int q = 0; q < K / 4; ++q) {
+        const uint32_t w[4] = { d[q].x, d[q].y, d[q].z, d[q].w };
+        uint32_t v[32];
+#pragma unroll
+        for (int wi = 0; wi < 4; ++wi) {
+            v[8 * wi + 0] = expand_word<false, 0>(w[wi]);
+            v[8 * wi + 1] = expand_word<false, 1>(w[wi]);
+            v[8 * wi + 2] = expand_word<false, 2>(w[wi]);
+            v[8 * wi + 3] = expand_word<false, 3>(w[wi]);
+            v[8 * wi + 4] = expand_word<false, 4>(w[wi]);
+            v[8 * wi + 5] = expand_word<false, 5>(w[wi]);
+            v[8 * wi + 6] = expand_word<false, 6>(w[wi]);
+            v[8 * wi + 7] = expand_word<false, 7>(w[wi]);
+        }
+        tc_store32(taddr + 32u * q, v);
+    }
+    tc_store_wait();
+}
+
+template<int K, bool NODUPES>
+__global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArgs p) {
+    constexpr int KA = K / 4;
+    constexpr int NS = V2_STAGES<K>;
+    constexpr int NA = V2_LEFT_BUFFERS<K>;
+    constexpr int NP = V2_PACKED;
+    constexpr int PACKED_BYTES = TN * K * 4;
+    constexpr uint32_t LEFT_COLS = 2 * 32 * KA; // both halves of one item
+    extern __shared__ uint8_t smem_raw[];
+    // stage full [NS], stage free [NS], packed full [NP], packed free [NP], accumulator full [3], drained [3], left full [NA]
+    __shared__ uint64_t bars[2 * NS + 2 * NP + 6 + NA];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int cols = p.cols;
+    const int ntiles = p.ntiles;
+    const int mpairs = p.mtiles; // here: ceil(cols / 256)
+    const long long item0 = p.items * blockIdx.x / gridDim.x;
+    const int nitems = (int)(p.items * (blockIdx.x + 1) / gridDim.x - item0);
+
+    const uint32_t s_b = (smem_u32(smem_raw) + 1023u) & ~1023u; // + stage * KA * ATOM_BYTES
+    const uint32_t s_packed = s_b + NS * KA * ATOM_BYTES;
+    const uint32_t bar_stage_full = smem_u32(&bars[0]);
+    const uint32_t bar_stage_free = bar_stage_full + 8 * NS;
+    const uint32_t bar_packed_full = bar_stage_free + 8 * NS;
+    const uint32_t bar_packed_free = bar_packed_full + 8 * NP;
+    const uint32_t bar_acc_full = bar_packed_free + 8 * NP;
+    const uint32_t bar_acc_drained = bar_acc_full + 24;
+    const uint32_t bar_left_full = bar_acc_drained + 24;
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(bar_stage_full + 8 * s, TN);
+            mbar_init(bar_stage_free + 8 * s, 1);
+        }
+        for (int s = 0; s < NP; ++s) {
+            mbar_init(bar_packed_full + 8 * s, 1);
+            mbar_init(bar_packed_free + 8 * s, TN);
+        }
+        for (int a = 0; a < 3; ++a) {
+            mbar_init(bar_acc_full + 8 * a, 1);
+            mbar_init(bar_acc_drained + 8 * a, TM);
+        }
+        for (int b = 0; b < NA; ++b)
+            mbar_init(bar_left_full + 8 * b, 2 * TM);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+
+    Item it;
+    it.decode(item0, p.rows, mpairs);
+
+    if (warp == 12) {
+        // ---- MMA issuer: the whole warp walks the tiles, one elected lane issues ----
+        {
+            const uint32_t u_tmem = uniform(tmem), u_sb = uniform(s_b);
+            int g = 0;
+            for (int n = 0; n < nitems; ++n) {
+                const int b = n % NA;
+                mbar_wait(bar_left_full + 8 * b, (n / NA) & 1);
+                for (int t = 0; t < ntiles; ++t, ++g) {
+                    const int s = g % NS;
+                    mbar_wait(bar_stage_full + 8 * s, (g / NS) & 1);
+                    const uint32_t sb = u_sb + (uint32_t)(s * KA * ATOM_BYTES);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int q = 2 * g + h, a = q % 3;
+                        if (q >= 3)
+                            mbar_wait(bar_acc_drained + 8 * a, (q / 3 - 1) & 1);
+                        tc_fence_after();
+                        const uint32_t left = u_tmem + V2_ACC_COLS + (uint32_t)(b * LEFT_COLS + h * 32 * KA);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int qa = 0; qa < KA; ++qa)
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+                                    tc_mma_i8_ts(
+                                        u_tmem + (uint32_t)(a * TN),
+                                        left + (uint32_t)(qa * 32 + kk * 8),
+                                        smem_desc(sb + qa * ATOM_BYTES + kk * 32),
+                                        IDESC,
+                                        (qa | kk) != 0
+                                    );
+                            tc_commit(bar_acc_full + 8 * a);
+                            if (h == 1)
+                                tc_commit(bar_stage_free + 8 * s);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    } else if (warp == 13) {
+        // ---- loader ----
+        if (tid == 13 * 32) {
+            int f = 0;
+            for (int n = 0; n < nitems; ++n) {
+                const uint32_t* const row = (it.dir ? p.left : p.right) + (size_t)it.row * p.pitch_words;
+                for (int t = 0; t < ntiles; ++t, ++f) {
+                    const int s = f % NP;
+                    if (f >= NP)
+                        mbar_wait(bar_packed_free + 8 * s, (f / NP - 1) & 1);
+                    const uint32_t bytes = (uint32_t)min(TN, cols - t * TN) * K * 4;
+                    mbar_expect_tx(bar_packed_full + 8 * s, bytes);
+                    bulk_copy_g2s(s_packed + (uint32_t)(s * PACKED_BYTES), row + (size_t)t * TN * K, bytes, bar_packed_full + 8 * s);
+                }
+                it.next(p.rows, mpairs);
+            }
+        }
+    } else if (warp >= 8) {
+        // ---- producers ----
+        const int r = tid - 2 * TM;
+        const int total = nitems * ntiles;
+        int t = 0;
+        for (int g = 0; g < total; ++g) {
+            const int ps = g % NP, s = g % NS;
+            const int valid = min(TN, cols - t * TN);
+            mbar_wait(bar_packed_full + 8 * ps, (g / NP) & 1);
+            uint4 d[KA];
+            const uint32_t src = s_packed + (uint32_t)(ps * PACKED_BYTES) + (uint32_t)min(r, valid - 1) * (K * 4);
+#pragma unroll
+            for (int q = 0; q < KA; ++q)
+                d[q] = ld_shared_v4(src + 16 * q);
+            if (g >= NS)
+                mbar_wait(bar_stage_free + 8 * s, (g / NS - 1) & 1);
+            expand_pixel<K, true>(d, s_b + (uint32_t)(s * KA * ATOM_BYTES), r);
+            mbar_arrive(bar_packed_free + 8 * ps); // after the stores that consumed the loaded registers
+            fence_async_smem();
+            mbar_arrive(bar_stage_full + 8 * s);
+            if (++t == ntiles)
+                t = 0;
+        }
+    } else {
+        // ---- epilogue: half h = warps 4h..4h+3, thread = TMEM lane = left pixel 256 mp + 128 h + lane ----
+        const int h = warp >> 2;
+        const int lane128 = tid & (TM - 1);
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        int pa_next = 0;
+        auto load_left = [&](const Item& at, uint4(&d)[KA]) {
+            const uint32_t* const row = (at.dir ? p.right : p.left) + (size_t)at.row * p.pitch_words;
+            load_pixel<K>(row + (size_t)min(at.mt * 2 * TM + h * TM + lane128, cols - 1) * K, d);
+        };
+        auto stage_left = [&](const uint4(&d)[KA], int n) {
+            const int b = n % NA;
+            expand_left_to_tmem<K>(d, lane_base + V2_ACC_COLS + (uint32_t)(b * LEFT_COLS + h * 32 * KA));
+            tc_fence_before();
+            mbar_arrive(bar_left_full + 8 * b);
+            int pc = 0;
+#pragma unroll
+            for (int q = 0; q < KA; ++q)
+                pc += __popc(d[q].x) + __popc(d[q].y) + __popc(d[q].z) + __popc(d[q].w);
+            return pc;
+        };
+        uint4 dl[KA];
+        if (nitems > 0) {
+            load_left(it, dl);
+            pa_next = stage_left(dl, 0);
+        }
+        int g = 0;
+        for (int n = 0; n < nitems; ++n) {
+            const int pa = pa_next;
+            Item nx = it;
+            nx.next(p.rows, mpairs);
+            int m_first = INT_MAX, m_last = INT_MAX;
+            if (n + 1 < nitems)
+                load_left(nx, dl);
+            for (int t = 0; t < ntiles; ++t, ++g) {
+                const int q = 2 * g + h, a = q % 3;
+                mbar_wait(bar_acc_full + 8 * a, (q / 3) & 1);
+                tc_fence_after();
+                const uint32_t acc = lane_base + (uint32_t)(a * TN);
+                const int tile0 = t * TN;
+                int va[32], vb[32];
+                if (tile0 + TN > cols) {
+                    TileMin32 m;
+#pragma unroll 1
+                    for (int u0 = 0; u0 < TN && tile0 + u0 < cols; u0 += 32) {
+                        tc_load32_issue(acc + (uint32_t)u0, va);
+                        tc_load32_wait(va);
+                        fold32_guarded<NODUPES>(va, u0, cols - tile0, m);
+                    }
+                    tc_fence_before();
+                    mbar_arrive(bar_acc_drained + 8 * a);
+                    merge_tile<NODUPES>(m, tile0, m_first, m_last);
+                } else if constexpr (K == 4) {
+                    TileMin16 m;
+                    tc_load64_packed_issue(acc, va);
+                    tc_load64_packed_issue(acc + 64, vb);
+                    tc_load32_wait(va);
+                    tc_load32_wait(vb);
+                    tc_fence_before();
+                    mbar_arrive(bar_acc_drained + 8 * a);
+                    fold64_packed<NODUPES, 0>(va, m);
+                    fold64_packed<NODUPES, 64>(vb, m);
+                    merge_tile<NODUPES>(m, tile0, m_first, m_last);
+                } else {
+                    TileMin32 m;
+                    tc_load32_issue(acc, va);
+                    tc_load32_wait(va);
+                    tc_load32_issue(acc + 32, vb);
+                    fold32<NODUPES, 0>(va, m);
+                    tc_load32_wait(vb);
+                    tc_load32_issue(acc + 64, va);
+                    fold32<NODUPES, 32>(vb, m);
+                    tc_load32_wait(va);
+                    tc_load32_issue(acc + 96, vb);
+                    fold32<NODUPES, 64>(va, m);
+                    tc_load32_wait(vb);
+                    tc_fence_before();
+                    mbar_arrive(bar_acc_drained + 8 * a);
+                    fold32<NODUPES, 96>(vb, m);
+                    merge_tile<NODUPES>(m, tile0, m_first, m_last);
+                }
+                // next item's left half: its TMEM columns are read only by this half's MMAs, all complete once
+                // this half's accumulator of the buffer's previous user (two buffers: the previous item, seen
+                // long ago; one: this item's last tile, just seen) has been committed
+                if (n + 1 < nitems && t == (NA == 2 ? min(2, ntiles - 1) : ntiles - 1))
+                    pa_next = stage_left(dl, n + 1);
+            }
+            const int i = it.mt * 2 * TM + h * TM + lane128;
+            if (i < cols) {
+                const size_t at = (size_t)it.row * cols + i;
+                (it.dir ? p.rev_first : p.fwd_first)[at] = ((uint32_t)(pa + (m_first >> COL_BITS)) << 16) | ((uint32_t)m_first & COL_MAX);
+                if constexpr (NODUPES)
+                    (it.dir ? p.rev_last : p.fwd_last)[at] =
+                        ((uint32_t)(pa + (m_last >> COL_BITS)) << 16) | ((65535u - COL_MAX) + ((uint32_t)m_last & COL_MAX));
+            }
+            it = nx;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+template<int K>
+constexpr int v2_smem_bytes() {
+    return V2_STAGES<K> * (K / 4) * ATOM_BYTES + V2_PACKED * TN * K * 4 + 1024;
+}
+
+template<int K, bool NODUPES>
+cudaError_t launch_k2(MmaArgs p, int dirs, cudaStream_t stream) {
+    constexpr int smem = v2_smem_bytes<K>();
+    auto kernel = search_mma2_kernel<K, NODUPES>;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess)
+        return err;
+    static thread_local int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if ((err = cudaGetDevice(&dev)) != cudaSuccess)
+            return err;
+        if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
+            return err;
+    }
+    p.mtiles = (p.cols + 2 * TM - 1) / (2 * TM); // M pairs
+    p.items = (long long)dirs * p.rows * p.mtiles;
+    if (p.items > 0x7FFFFFFFLL)
+        return cudaErrorInvalidConfiguration;
+    const unsigned grid = (unsigned)(p.items < sms ? p.items : sms);
+    kernel<<<grid, V2_THREADS, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
 template<int K, bool NODUPES>
 cudaError_t launch_k(MmaArgs p, int dirs, cudaStream_t stream) {
     const int smem = search_mma_smem_bytes(K);
@@ -647,6 +1020,24 @@ int search_mma_smem_bytes(int K) {
     return (lefts + stages) * (K / 4) * ATOM_BYTES + packed * TN * K * 4 + 1024; // left tiles, right stages, packed ring, alignment slack
 }
 
+namespace {
+int g_variant = -1;
+}
+
+// 1 = two CTAs per SM, both operands in shared memory; 2 = one CTA per SM, left operand in tensor memory
+// (128 / 256 bits). Environment BICOS_B200_MMA_VARIANT overrides the default for A/B timing.
+int search_mma_variant() {
+    if (g_variant < 0) {
+        const char* v = getenv("BICOS_B200_MMA_VARIANT");
+        g_variant = v && v[0] == '2' ? 2 : 1;
+    }
+    return g_variant;
+}
+
+void set_search_mma_variant(int v) {
+    g_variant = v == 2 ? 2 : 1;
+}
+
 bool search_mma_supports(int K, int cols) {
     return (K == 4 || K == 8 || K == 12 || K == 16) && cols >= 1 && cols <= COL_MAX + 1;
 }
@@ -681,6 +1072,10 @@ cudaError_t launch_search_mma(
     p.rev_last = rev_last;
     const int dirs = (flags & FLAG_CONSISTENCY) ? 2 : 1;
     const bool nodupes = (flags & FLAG_NODUPES) != 0;
+    if (search_mma_variant() == 2 && K == 4)
+        return nodupes ? launch_k2<4, true>(p, dirs, stream) : launch_k2<4, false>(p, dirs, stream);
+    if (search_mma_variant() == 2 && K == 8)
+        return nodupes ? launch_k2<8, true>(p, dirs, stream) : launch_k2<8, false>(p, dirs, stream);
     switch (K) {
         case 4:
             return nodupes ? launch_k<4, true>(p, dirs, stream) : launch_k<4, false>(p, dirs, stream);

@@ -1,11 +1,14 @@
 cd /root/repo
-run() { echo "== $*"; timeout 60 tools/search_engines "$@" 2>&1 | grep "^cols\|error"; }
-run 4096 1 8 1 0
-run 4096 4 8 1 0
-run 256 400 8 1 0
-run 256 400 8 0 0
-run 512 400 8 0 0
-run 256 400 12 1 0
-run 256 400 16 1 0
-run 256 400 4 1 0
-run 2448 16 8 0 0
+run() { timeout 60 tools/search_engines "$@" 2>&1 | grep "^cols\|rror\|row" | head -8; }
+for v in 1 2; do
+run 256 4 4 3 0 64 $v
+run 1000 8 4 3 1 64 $v
+run 2448 16 8 3 3 64 $v
+run 300 500 8 2 1 64 $v
+run 384 700 4 3 1 64 $v
+run 2048 1536 4 2 3 64 $v
+run 2048 1536 4 1 3 64 $v
+run 4096 750 8 1 2 64 $v
+done
+run 600 40 12 3 1 64 1
+run 600 40 16 3 1 64 1

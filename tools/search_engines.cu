@@ -1,5 +1,5 @@
 // Parity and timing of the two search engines on the same descriptors:
-//   search_engines COLS ROWS K FLAGS [REPS] [POOL]
+//   search_engines COLS ROWS K FLAGS [REPS] [POOL] [MMA_VARIANT]
 // Descriptors are drawn from a small pool with a few flipped bits, so that exact ties (the
 // no-duplicates case) and near ties are frequent. The popcount engine (search.cu) is itself
 // pinned to the oracle by tests/test_gpu_parity.py; here the tensor-core engine (search_mma.cu)
@@ -30,6 +30,8 @@ int main(int argc, char** argv) {
     const int flags = argc > 4 ? std::atoi(argv[4]) : 3;
     const int reps = argc > 5 ? std::atoi(argv[5]) : 5;
     const int pool = argc > 6 ? std::atoi(argv[6]) : 64;
+    if (argc > 7)
+        set_search_mma_variant(std::atoi(argv[7])); // else: default / BICOS_B200_MMA_VARIANT
 
     const size_t pitch = ((size_t)cols * K + 3) / 4 * 4;
     std::mt19937 rng(1234u + cols + 7 * rows + 13 * K);
@@ -118,8 +120,8 @@ int main(int argc, char** argv) {
             ties += (a[i] & 0xFFFF) != 65535u - (a[px + i] & 0xFFFF);
     const double pairs = (double)rows * cols * cols * ((flags & FLAG_CONSISTENCY) ? 1 : 1);
     std::printf(
-        "cols %d rows %d K %d flags %d: popc %.4f ms (%.3f Tpair/s), mma %.4f ms (%.3f Tpair/s), speed-up %.2fx, forward ties %lld, %s\n",
-        cols, rows, K, flags, ms[0], pairs / ms[0] * 1e-9, ms[1], pairs / ms[1] * 1e-9, ms[1] > 0 ? ms[0] / ms[1] : 0.0, ties,
+        "cols %d rows %d K %d flags %d variant %d: popc %.4f ms (%.3f Tpair/s), mma %.4f ms (%.3f Tpair/s), speed-up %.2fx, forward ties %lld, %s\n",
+        cols, rows, K, flags, search_mma_variant(), ms[0], pairs / ms[0] * 1e-9, ms[1], pairs / ms[1] * 1e-9, ms[1] > 0 ? ms[0] / ms[1] : 0.0, ties,
         bad_total ? "MISMATCH" : "identical"
     );
     return bad_total ? 1 : 0;
