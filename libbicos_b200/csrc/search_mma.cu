@@ -41,6 +41,7 @@
 #include "kernels.cuh"
 
 #include <limits.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace bicos_b200 {
@@ -85,8 +86,13 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 // error the C ABI reports) instead of spinning forever.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins)
-        if (spins > (1u << 20))
+        if (spins > (1u << 20)) {
+#ifdef BICOS_MMA_DEBUG
+            printf("mbar timeout: block %d warp %d lane %d barrier +%u parity %u\n", blockIdx.x, threadIdx.x >> 5, threadIdx.x & 31,
+                   bar & 1023u, parity);
+#endif
             __trap();
+        }
 }
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -474,30 +480,35 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
     it.decode(item0, p.rows, p.mtiles);
 
     if (warp == 8) {
-        // ---- MMA issuer: the whole warp walks the tiles, one elected lane issues ----
+        // ---- MMA issuer: the whole warp walks the tiles, one elected lane issues. Stage / accumulator
+        //      indices and barrier phases are carried incrementally and the descriptors differ from a
+        //      per-stage base by constants: this loop's own latency bounds the kernel otherwise. ----
         {
-            const uint32_t u_tmem = uniform(tmem), u_sa = uniform(s_a), u_sb = uniform(s_b);
-            int g = 0; // tiles issued by this CTA
+            const uint32_t u_tmem = uniform(tmem);
+            const uint64_t desc_a0 = smem_desc(uniform(s_a)), desc_b0 = smem_desc(uniform(s_b));
+            constexpr uint32_t STAGE_STEP = (KA * ATOM_BYTES) >> 4; // descriptor start-address units (16 B)
+            uint32_t s = 0, stage_phase = 0; // stage of tile g and the parity its "full" barrier completes with
+            uint32_t a = 0; // accumulator g & 1
+            uint32_t b = 0, left_phase = 0;
+            int g = 0;
             for (int n = 0; n < nitems; ++n) {
-                const int b = n % NA;
-                mbar_wait(bar_left_full + 8 * b, (n / NA) & 1);
-                const uint32_t sa = u_sa + (uint32_t)(b * KA * ATOM_BYTES);
+                mbar_wait(bar_left_full + 8 * b, left_phase);
+                const uint64_t desc_a = desc_a0 + b * STAGE_STEP;
                 for (int t = 0; t < ntiles; ++t, ++g) {
-                    const int s = g % NS, a = g & 1;
-                    mbar_wait(bar_stage_full + 8 * s, (g / NS) & 1);
+                    mbar_wait(bar_stage_full + 8 * s, stage_phase);
                     if (g >= 2)
                         mbar_wait(bar_acc_drained + 8 * a, ((g - 2) >> 1) & 1); // the epilogue has read this accumulator
                     tc_fence_after();
-                    const uint32_t sb = u_sb + (uint32_t)(s * KA * ATOM_BYTES);
+                    const uint64_t desc_b = desc_b0 + s * STAGE_STEP;
                     if (elect_one()) {
 #pragma unroll
                         for (int q = 0; q < KA; ++q)
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk)
                                 tc_mma_i8(
-                                    u_tmem + (uint32_t)(a * TN),
-                                    smem_desc(sa + q * ATOM_BYTES + kk * 32),
-                                    smem_desc(sb + q * ATOM_BYTES + kk * 32),
+                                    u_tmem + a * TN,
+                                    desc_a + (uint32_t)((q * ATOM_BYTES + kk * 32) >> 4),
+                                    desc_b + (uint32_t)((q * ATOM_BYTES + kk * 32) >> 4),
                                     IDESC,
                                     (q | kk) != 0
                                 );
@@ -505,6 +516,15 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
                         tc_commit(bar_acc_full + 8 * a);
                     }
                     __syncwarp();
+                    if (++s == NS) {
+                        s = 0;
+                        stage_phase ^= 1;
+                    }
+                    a ^= 1;
+                }
+                if (++b == NA) {
+                    b = 0;
+                    left_phase ^= 1;
                 }
             }
         }
@@ -672,8 +692,8 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
 // 128 x 128 of output). TMEM: three 128-column accumulators in rotation (columns 0..383) + the left
 // operand, 2 x 32 columns per 128 descriptor bits, double-buffered for 128 bits (columns 384..511).
 //   warps 0-3 / 4-7  epilogue of the first / second 128 left pixels (the four lane quadrants each)
-//   warps 8-11       producers        warp 12  MMA issuer        warp 13  loader
-constexpr int V2_THREADS = 448;
+//   warps 8-11       producers        warps 12, 13  MMA issuers (one per half)        warp 14  loader
+constexpr int V2_THREADS = 480;
 constexpr uint32_t V2_ACC_COLS = 3 * TN;
 template<int K>
 constexpr int V2_STAGES = K == 4 ? 8 : 4; // 128 KB of right tiles
@@ -713,8 +733,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
     constexpr int PACKED_BYTES = TN * K * 4;
     constexpr uint32_t LEFT_COLS = 2 * 32 * KA; // both halves of one item
     extern __shared__ uint8_t smem_raw[];
-    // stage full [NS], stage free [NS], packed full [NP], packed free [NP], accumulator full [3], drained [3], left full [NA]
-    __shared__ uint64_t bars[2 * NS + 2 * NP + 6 + NA];
+    // stage full [NS], stage free [NS], packed full [NP], packed free [NP], accumulator full [3][2], drained [3][2],
+    // left full [NA]. The accumulator barriers are per (accumulator, half): group q = 2 g + h uses accumulator
+    // q % 3, so an accumulator alternates between the halves; with one barrier per accumulator each waiter would
+    // see only every second phase, and a parity wait two phases ahead of the barrier succeeds at once.
+    __shared__ uint64_t bars[2 * NS + 2 * NP + 12 + NA];
     __shared__ uint32_t tmem_base_slot;
 
     const int tid = threadIdx.x;
@@ -732,19 +755,19 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
     const uint32_t bar_packed_full = bar_stage_free + 8 * NS;
     const uint32_t bar_packed_free = bar_packed_full + 8 * NP;
     const uint32_t bar_acc_full = bar_packed_free + 8 * NP;
-    const uint32_t bar_acc_drained = bar_acc_full + 24;
-    const uint32_t bar_left_full = bar_acc_drained + 24;
+    const uint32_t bar_acc_drained = bar_acc_full + 48; // + 8 * (2 * accumulator + half)
+    const uint32_t bar_left_full = bar_acc_drained + 48;
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
             mbar_init(bar_stage_full + 8 * s, TN);
-            mbar_init(bar_stage_free + 8 * s, 1);
+            mbar_init(bar_stage_free + 8 * s, 2);
         }
         for (int s = 0; s < NP; ++s) {
             mbar_init(bar_packed_full + 8 * s, 1);
             mbar_init(bar_packed_free + 8 * s, TN);
         }
-        for (int a = 0; a < 3; ++a) {
+        for (int a = 0; a < 6; ++a) {
             mbar_init(bar_acc_full + 8 * a, 1);
             mbar_init(bar_acc_drained + 8 * a, TM);
         }
@@ -765,49 +788,57 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
     Item it;
     it.decode(item0, p.rows, mpairs);
 
-    if (warp == 12) {
-        // ---- MMA issuer: the whole warp walks the tiles, one elected lane issues ----
+    if (warp == 12 || warp == 13) {
+        // ---- MMA issuers: warp 12 + h issues the MMAs of left half h (whole warp, one elected lane).
+        //      Two issuers because the issue loop's own latency, not the tensor pipe, bounds a single one. ----
         {
-            const uint32_t u_tmem = uniform(tmem), u_sb = uniform(s_b);
-            int g = 0;
+            const int h = warp - 12;
+            const uint32_t u_tmem = uniform(tmem);
+            const uint64_t desc_b0 = smem_desc(uniform(s_b));
+            constexpr uint32_t STAGE_STEP = (KA * ATOM_BYTES) >> 4;
+            uint32_t s = 0, stage_phase = 0;
+            uint32_t b = 0, left_phase = 0;
+            int q = h; // MMA group 2 g + h
             for (int n = 0; n < nitems; ++n) {
-                const int b = n % NA;
-                mbar_wait(bar_left_full + 8 * b, (n / NA) & 1);
-                for (int t = 0; t < ntiles; ++t, ++g) {
-                    const int s = g % NS;
-                    mbar_wait(bar_stage_full + 8 * s, (g / NS) & 1);
-                    const uint32_t sb = u_sb + (uint32_t)(s * KA * ATOM_BYTES);
+                mbar_wait(bar_left_full + 8 * b, left_phase);
+                const uint32_t left = u_tmem + V2_ACC_COLS + b * LEFT_COLS + (uint32_t)(h * 32 * KA);
+                for (int t = 0; t < ntiles; ++t, q += 2) {
+                    const uint32_t a = (uint32_t)q % 3u;
+                    mbar_wait(bar_stage_full + 8 * s, stage_phase);
+                    if (q >= 3) // the accumulator's previous use, by the other half, has been read
+                        mbar_wait(bar_acc_drained + 8 * (2 * a + (1 - h)), (((uint32_t)q - 3u) / 6u) & 1u);
+                    tc_fence_after();
+                    const uint64_t desc_b = desc_b0 + s * STAGE_STEP;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int q = 2 * g + h, a = q % 3;
-                        if (q >= 3)
-                            mbar_wait(bar_acc_drained + 8 * a, (q / 3 - 1) & 1);
-                        tc_fence_after();
-                        const uint32_t left = u_tmem + V2_ACC_COLS + (uint32_t)(b * LEFT_COLS + h * 32 * KA);
-                        if (elect_one()) {
+                        for (int qa = 0; qa < KA; ++qa)
 #pragma unroll
-                            for (int qa = 0; qa < KA; ++qa)
-#pragma unroll
-                                for (int kk = 0; kk < 4; ++kk)
-                                    tc_mma_i8_ts(
-                                        u_tmem + (uint32_t)(a * TN),
-                                        left + (uint32_t)(qa * 32 + kk * 8),
-                                        smem_desc(sb + qa * ATOM_BYTES + kk * 32),
-                                        IDESC,
-                                        (qa | kk) != 0
-                                    );
-                            tc_commit(bar_acc_full + 8 * a);
-                            if (h == 1)
-                                tc_commit(bar_stage_free + 8 * s);
-                        }
-                        __syncwarp();
+                            for (int kk = 0; kk < 4; ++kk)
+                                tc_mma_i8_ts(
+                                    u_tmem + a * TN,
+                                    left + (uint32_t)(qa * 32 + kk * 8),
+                                    desc_b + (uint32_t)((qa * ATOM_BYTES + kk * 32) >> 4),
+                                    IDESC,
+                                    (qa | kk) != 0
+                                );
+                        tc_commit(bar_acc_full + 8 * (2 * a + h));
+                        tc_commit(bar_stage_free + 8 * s); // counts 2: both halves have read the stage
                     }
+                    __syncwarp();
+                    if (++s == NS) {
+                        s = 0;
+                        stage_phase ^= 1;
+                    }
+                }
+                if (++b == NA) {
+                    b = 0;
+                    left_phase ^= 1;
                 }
             }
         }
-    } else if (warp == 13) {
+    } else if (warp == 14) {
         // ---- loader ----
-        if (tid == 13 * 32) {
+        if (tid == 14 * 32) {
             int f = 0;
             for (int n = 0; n < nitems; ++n) {
                 const uint32_t* const row = (it.dir ? p.left : p.right) + (size_t)it.row * p.pitch_words;
@@ -881,7 +912,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
                 load_left(nx, dl);
             for (int t = 0; t < ntiles; ++t, ++g) {
                 const int q = 2 * g + h, a = q % 3;
-                mbar_wait(bar_acc_full + 8 * a, (q / 3) & 1);
+                mbar_wait(bar_acc_full + 8 * (2 * a + h), ((uint32_t)q / 6u) & 1u);
                 tc_fence_after();
                 const uint32_t acc = lane_base + (uint32_t)(a * TN);
                 const int tile0 = t * TN;
@@ -895,7 +926,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
                         fold32_guarded<NODUPES>(va, u0, cols - tile0, m);
                     }
                     tc_fence_before();
-                    mbar_arrive(bar_acc_drained + 8 * a);
+                    mbar_arrive(bar_acc_drained + 8 * (2 * a + h));
                     merge_tile<NODUPES>(m, tile0, m_first, m_last);
                 } else if constexpr (K == 4) {
                     TileMin16 m;
@@ -904,7 +935,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
                     tc_load32_wait(va);
                     tc_load32_wait(vb);
                     tc_fence_before();
-                    mbar_arrive(bar_acc_drained + 8 * a);
+                    mbar_arrive(bar_acc_drained + 8 * (2 * a + h));
                     fold64_packed<NODUPES, 0>(va, m);
                     fold64_packed<NODUPES, 64>(vb, m);
                     merge_tile<NODUPES>(m, tile0, m_first, m_last);
@@ -922,7 +953,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
                     fold32<NODUPES, 64>(va, m);
                     tc_load32_wait(vb);
                     tc_fence_before();
-                    mbar_arrive(bar_acc_drained + 8 * a);
+                    mbar_arrive(bar_acc_drained + 8 * (2 * a + h));
                     fold32<NODUPES, 96>(vb, m);
                     merge_tile<NODUPES>(m, tile0, m_first, m_last);
                 }
@@ -1025,17 +1056,20 @@ int g_variant = -1;
 }
 
 // 1 = two CTAs per SM, both operands in shared memory; 2 = one CTA per SM, left operand in tensor memory
-// (128 / 256 bits). Environment BICOS_B200_MMA_VARIANT overrides the default for A/B timing.
+// (128 / 256 bits); 0 = automatic: 2 where it applies and the image has an item for every SM (measured on
+// the B200: 1.25 against 1.34 ms on the metric configuration, 2.35 against 2.63 ms for 256 bits x 4096
+// columns; small images are served better by the finer items of variant 1). Environment
+// BICOS_B200_MMA_VARIANT = 1 | 2 overrides for A/B timing.
 int search_mma_variant() {
     if (g_variant < 0) {
         const char* v = getenv("BICOS_B200_MMA_VARIANT");
-        g_variant = v && v[0] == '2' ? 2 : 1;
+        g_variant = v && v[0] == '2' ? 2 : v && v[0] == '1' ? 1 : 0;
     }
     return g_variant;
 }
 
 void set_search_mma_variant(int v) {
-    g_variant = v == 2 ? 2 : 1;
+    g_variant = v == 2 ? 2 : v == 1 ? 1 : 0;
 }
 
 bool search_mma_supports(int K, int cols) {
@@ -1072,9 +1106,12 @@ cudaError_t launch_search_mma(
     p.rev_last = rev_last;
     const int dirs = (flags & FLAG_CONSISTENCY) ? 2 : 1;
     const bool nodupes = (flags & FLAG_NODUPES) != 0;
-    if (search_mma_variant() == 2 && K == 4)
+    const long long pair_items = (long long)dirs * rows * ((cols + 2 * TM - 1) / (2 * TM));
+    const int variant = search_mma_variant();
+    const bool v2 = (K == 4 || K == 8) && (variant == 2 || (variant == 0 && pair_items >= 2 * 148));
+    if (v2 && K == 4)
         return nodupes ? launch_k2<4, true>(p, dirs, stream) : launch_k2<4, false>(p, dirs, stream);
-    if (search_mma_variant() == 2 && K == 8)
+    if (v2 && K == 8)
         return nodupes ? launch_k2<8, true>(p, dirs, stream) : launch_k2<8, false>(p, dirs, stream);
     switch (K) {
         case 4:
