@@ -373,16 +373,16 @@ def main():
     int8_peak, int8_src = measure_int8_peak()
     dirs = 2  # Consistency: forward and reverse search, each a full W x W x 128 product per row
     mma_ops = 2.0 * COLS * px * 32 * K * dirs
-    smem_bytes = (COLS / 128) * (px / 128) * dirs * 52 * 1024  # per 128x128 tile: 32 KB operand reads, 16 KB expansion, 4 KB packed ring
+    smem_bytes = (COLS / 128) * (px / 128) * dirs * 26 * 1024  # variant 2, per 128x128 tile: 16 KB operand reads, 8 KB expansion, 2 KB packed ring
     mma_line = {
-        "kernel": "search_mma_kernel<4, CONSISTENCY>", "bound": "tensor", "achieved": mma_ops / t_mma / 1e12,
+        "kernel": "search_mma2_kernel<4, CONSISTENCY>", "bound": "tensor", "achieved": mma_ops / t_mma / 1e12,
         "peak": int8_peak, "unit": "TOP/s", "frac": mma_ops / t_mma / 1e12 / int8_peak, "traffic": traffic.get("search_mma"),
         "peak_source": int8_src, "ms_per_launch": t_mma * 1e3,
         "smem_frac": smem_bytes / t_mma / (128.0 * 148 * sm_max * 1e6),
         "note": "the tensor-core engine (default): W x W x 128-bit Hamming matrix per row and direction as int8 tcgen05.mma "
                 "(kind::i8, TMEM accumulators), argmin in the epilogue; achieved = 2*W*P*bits*directions int8 ops per "
-                "launch over the stage time. smem_frac: shared-memory bytes the kernel moves (operand reads of the MMAs + "
-                "operand expansion) over 128 B/clk/SM - the resource ncu shows closest to its limit",
+                "launch over the stage time. smem_frac: shared-memory bytes the kernel moves (streamed-operand reads of the MMAs, "
+                "the resident operand lives in TMEM, + operand expansion) over 128 B/clk/SM",
     }
     roofline = mma_line if tensor else popc_line
     roofline["engine"] = "tensor" if tensor else "popc"
