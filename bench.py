@@ -31,9 +31,12 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly one JSON line. Libraries write to file descriptor 1 behind Python's back (NCCL prints
+# its version banner there at every level from VERSION up, WARN included): Python's sys.stdout keeps a duplicate
+# of the original descriptor, and descriptor 1 itself is pointed at stderr for everything else.
+sys.stdout.flush()
+sys.stdout = os.fdopen(os.dup(1), "w", buffering=1)
+os.dup2(2, 1)
 
 N_IMAGES, ROWS, COLS = 33, 1536, 2048
 FRAMES = 4  # distinct stereo stacks per GPU per step (4 x 208 MB of input > 126 MB L2)
