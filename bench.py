@@ -382,6 +382,10 @@ def main():
         "peak": int8_peak, "unit": "TOP/s", "frac": mma_ops / t_mma / 1e12 / int8_peak, "traffic": traffic.get("search_mma"),
         "peak_source": int8_src, "ms_per_launch": t_mma * 1e3,
         "smem_frac": smem_bytes / t_mma / (128.0 * 148 * sm_max * 1e6),
+        # SURVEY 8d scores the search in popc32 (S = W * P * K) against the POPC pipe, the bound of a popcount kernel:
+        # the same algorithmic work over this engine's time, for comparison with that table
+        "algorithmic_popc32": {"achieved": popc_alg / t_mma / 1e12, "peak": popc_peak / 1e12, "unit": "Tpopc32/s",
+                               "frac": popc_alg / t_mma / popc_peak, "peak_source": popc_src},
         "note": "the tensor-core engine (default): W x W x 128-bit Hamming matrix per row and direction as int8 tcgen05.mma "
                 "(kind::i8, TMEM accumulators), argmin in the epilogue; achieved = 2*W*P*bits*directions int8 ops per "
                 "launch over the stage time. smem_frac: shared-memory bytes the kernel moves (streamed-operand reads of the MMAs, "
