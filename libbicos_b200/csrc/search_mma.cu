@@ -23,20 +23,24 @@
 // VIADDMNMX.S16x2 folds two pairs (the popcount engine needs 3 POPC + 6 LOP3 + 5 more per pair);
 // wider descriptors use the 32-bit VIADDMNMX, one pair per instruction.
 // The reverse search of the consistency check (bicos.hpp:99-106) is the same kernel with the
-// operands swapped (grid.y = 2): on the tensor cores the second W x W x KBITS product is
-// cheaper than column-wise minima of the first.
+// operands swapped (the second half of the work items): on the tensor cores the second
+// W x W x KBITS product is cheaper than column-wise minima of the first.
 //
-// One CTA = 128 left pixels of one row (the 128 TMEM lanes) against the whole right row in
-// tiles of 128 columns. 288 threads, three roles:
-//   warps 4-7  producers: packed right descriptors of a tile -> uint8 in shared memory
-//              (128B-swizzled K-major, the layout TMA would produce), 2-4 stages, the next
-//              tile's descriptors already in registers
-//   warp 8     one thread issues KBITS/32 tcgen05.mma (128 x 128 x 32, kind::i8) per tile into one
-//              of two TMEM accumulators and commits to the stage / accumulator mbarriers
-//   warps 0-3  expand the left tile once, then per tile: tcgen05.ld their lane quadrant (the next
-//              half in flight while one is folded), fold it into the running minima, hand the
-//              accumulator back
-// Shared memory: (1 + stages) x KBITS/128 x 16 KB; TMEM: 2 x 128 columns.
+// Persistent CTAs walk contiguous ranges of work items (direction, row, M tile); within a CTA four
+// roles are hand-shaken by mbarriers only:
+//   loader     one thread: TMA bulk copies of the packed descriptors of the next 128-column tile
+//              into a small ring, across item boundaries (no global loads in the producers: the
+//              fence that publishes a tile to the async proxy waits for all loads of its thread)
+//   producers  4 warps: one packed descriptor per thread -> a 128-byte row of the uint8 tile in
+//              shared memory (128B-swizzled K-major, the layout a tensor-map TMA load would produce)
+//   issuer     a whole warp with uniform control flow, one elected lane issuing KBITS/32 tcgen05.mma
+//              (128 x 128 x 32, kind::i8) per tile and the commits to the stage / accumulator barriers
+//   epilogue   4 warps per 128 left pixels (the four TMEM lane quadrants): tcgen05.ld the accumulator,
+//              hand it back, fold it into the running minima; expand the next item's left tile in passing
+// Two kernels: search_mma_kernel (every width; 2 CTAs per SM up to 256 bits; 128 left pixels per item,
+// both operands in shared memory, 2 accumulators) and search_mma2_kernel (128 / 256 bits, large images;
+// 1 CTA per SM, 256 left pixels per item, left operand resident in TMEM, 3 accumulators in rotation,
+// one issuer per half). DESIGN.md 3.2a has the measurements that led from one to the other.
 
 #include "kernels.cuh"
 
