@@ -987,6 +987,17 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
     }
 }
 
+int sm_count_of_current_device() {
+    static thread_local int cached_dev = -1, cached_sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev != cached_dev) {
+        if (cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            cached_sms = 148;
+        cached_dev = dev;
+    }
+    return cached_sms;
+}
+
 template<int K>
 constexpr int v2_smem_bytes() {
     return V2_STAGES<K> * (K / 4) * ATOM_BYTES + V2_PACKED * TN * K * 4 + 1024;
@@ -999,14 +1010,7 @@ cudaError_t launch_k2(MmaArgs p, int dirs, cudaStream_t stream) {
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess)
         return err;
-    static thread_local int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if ((err = cudaGetDevice(&dev)) != cudaSuccess)
-            return err;
-        if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
-            return err;
-    }
+    const int sms = sm_count_of_current_device();
     p.mtiles = (p.cols + 2 * TM - 1) / (2 * TM); // M pairs
     p.items = (long long)dirs * p.rows * p.mtiles;
     if (p.items > 0x7FFFFFFFLL)
@@ -1027,17 +1031,10 @@ cudaError_t launch_k(MmaArgs p, int dirs, cudaStream_t stream) {
     // of search_mma_smem_bytes are laid out for 2 per SM up to 256 bits, 1 beyond; the occupancy API
     // reports 1 for the 2-CTA variants until the carve-out is raised, so it is not asked), each walking a
     // contiguous share of the items
-    static thread_local int resident = 0; // per template instance
-    if (resident == 0) {
-        int dev = 0, sms = 0;
-        if ((err = cudaGetDevice(&dev)) != cudaSuccess)
-            return err;
-        if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
-            return err;
-        if ((err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
-            return err;
-        resident = sms * (K <= 8 ? 2 : 1);
-    }
+    // (function attributes are per device: set on every launch, like the shared-memory size)
+    if ((err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
+        return err;
+    const int resident = sm_count_of_current_device() * (K <= 8 ? 2 : 1);
     p.items = (long long)dirs * p.rows * p.mtiles;
     if (p.items > 0x7FFFFFFFLL)
         return cudaErrorInvalidConfiguration;
@@ -1096,6 +1093,8 @@ cudaError_t launch_search_mma(
 ) {
     if (rows <= 0 || !search_mma_supports(K, cols))
         return cudaErrorInvalidValue;
+    if ((((uintptr_t)desc0 | (uintptr_t)desc1) & 15) != 0 || (desc_pitch_words & 3) != 0)
+        return cudaErrorMisalignedAddress; // the loader's bulk copies move 16-byte units
     MmaArgs p;
     p.left = desc0;
     p.right = desc1;
@@ -1112,7 +1111,7 @@ cudaError_t launch_search_mma(
     const bool nodupes = (flags & FLAG_NODUPES) != 0;
     const long long pair_items = (long long)dirs * rows * ((cols + 2 * TM - 1) / (2 * TM));
     const int variant = search_mma_variant();
-    const bool v2 = (K == 4 || K == 8) && (variant == 2 || (variant == 0 && pair_items >= 2 * 148));
+    const bool v2 = (K == 4 || K == 8) && (variant == 2 || (variant == 0 && pair_items >= 2 * sm_count_of_current_device()));
     if (v2 && K == 4)
         return nodupes ? launch_k2<4, true>(p, dirs, stream) : launch_k2<4, false>(p, dirs, stream);
     if (v2 && K == 8)
