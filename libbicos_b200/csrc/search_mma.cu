@@ -998,6 +998,36 @@ int sm_count_of_current_device() {
     return cached_sms;
 }
 
+// Function attributes are per device and cost a driver call each: set once per (kernel, device, thread).
+cudaError_t configure_once(void (*kernel)(const MmaArgs), int smem) {
+    struct Entry {
+        void (*kernel)(const MmaArgs);
+        unsigned long long devices; // one bit per device ordinal
+    };
+    static thread_local Entry cache[16] = {};
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess)
+        return err;
+    Entry* e = nullptr;
+    for (Entry& c: cache)
+        if (c.kernel == kernel || c.kernel == nullptr) {
+            e = &c;
+            break;
+        }
+    if (e && e->kernel == kernel && dev < 64 && ((e->devices >> dev) & 1ull))
+        return cudaSuccess;
+    if ((err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
+        return err;
+    if ((err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
+        return err;
+    if (e && dev < 64) {
+        e->kernel = kernel;
+        e->devices |= 1ull << dev;
+    }
+    return cudaSuccess;
+}
+
 template<int K>
 constexpr int v2_smem_bytes() {
     return V2_STAGES<K> * (K / 4) * ATOM_BYTES + V2_PACKED * TN * K * 4 + 1024;
@@ -1007,7 +1037,7 @@ template<int K, bool NODUPES>
 cudaError_t launch_k2(MmaArgs p, int dirs, cudaStream_t stream) {
     constexpr int smem = v2_smem_bytes<K>();
     auto kernel = search_mma2_kernel<K, NODUPES>;
-    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t err = configure_once(kernel, smem);
     if (err != cudaSuccess)
         return err;
     const int sms = sm_count_of_current_device();
@@ -1024,16 +1054,13 @@ template<int K, bool NODUPES>
 cudaError_t launch_k(MmaArgs p, int dirs, cudaStream_t stream) {
     const int smem = search_mma_smem_bytes(K);
     auto kernel = search_mma_kernel<K, NODUPES>;
-    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t err = configure_once(kernel, smem);
     if (err != cudaSuccess)
         return err;
     // persistent CTAs: as many as are resident at once (__launch_bounds__ and the shared-memory budget
     // of search_mma_smem_bytes are laid out for 2 per SM up to 256 bits, 1 beyond; the occupancy API
     // reports 1 for the 2-CTA variants until the carve-out is raised, so it is not asked), each walking a
     // contiguous share of the items
-    // (function attributes are per device: set on every launch, like the shared-memory size)
-    if ((err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess)
-        return err;
     const int resident = sm_count_of_current_device() * (K <= 8 ? 2 : 1);
     p.items = (long long)dirs * p.rows * p.mtiles;
     if (p.items > 0x7FFFFFFFLL)
