@@ -514,7 +514,8 @@ int do_match(
 
     KeyArrays ka = split_keys(static_cast<uint32_t*>(h->keys.ptr), px, flags);
     CU(cudaMemsetAsync(h->keys.ptr, 0xFF, px * sizeof(uint32_t) * n_keys, stream));
-    CU(launch_search(d0, d1, K, nrows, cols, dpw, flags, ka.fwd_first, ka.fwd_last, ka.rev_first, ka.rev_last, stream));
+    // descriptors of our own transform: 4n - 6 or n^2 - 2n + 3 bits, never all 32 K, so the top bit is free
+    CU(launch_search(d0, d1, K, nrows, cols, dpw, flags, ka.fwd_first, ka.fwd_last, ka.rev_first, ka.rev_last, stream, true));
     h->launches += 1;
     if (int rc = prof_mark(h, stream))
         return rc;

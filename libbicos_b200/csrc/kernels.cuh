@@ -88,7 +88,8 @@ cudaError_t launch_search(
     uint32_t* fwd_last,
     uint32_t* rev_first,
     uint32_t* rev_last,
-    cudaStream_t stream
+    cudaStream_t stream,
+    bool top_bit_free = false
 );
 
 // The two engines behind launch_search. `popc` (search.cu): XOR + POPC on the integer pipes, any
@@ -122,8 +123,11 @@ cudaError_t launch_search_mma(
     uint32_t* fwd_last,
     uint32_t* rev_first,
     uint32_t* rev_last,
-    cudaStream_t stream
+    cudaStream_t stream,
+    bool top_bit_free = false // bit 32 K - 1 is zero in every descriptor (true for the transform's output)
 );
+bool search_mma_colterm(); // see search_mma.cu, fold32
+void set_search_mma_colterm(bool on);
 bool search_mma_supports(int K, int cols);
 int search_mma_smem_bytes(int K);
 int search_mma_variant(); // tensor-core kernel variant, see search_mma.cu

@@ -58,6 +58,9 @@ constexpr int ATOM_BYTES = 128 * 128; // 128 pixels x 128 descriptor bits as int
 constexpr uint32_t TMEM_COLS = 2 * TN;
 constexpr int COL_BITS = 13; // merged keys step by 8192 per unit of Hamming distance
 constexpr int COL_MAX = (1 << COL_BITS) - 1;
+#ifndef BICOS_MMA_COLTERM_DEFAULT
+#define BICOS_MMA_COLTERM_DEFAULT 0 // not yet validated on the device: opt-in
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -261,7 +264,7 @@ __device__ __forceinline__ uint32_t expand_word(uint32_t w) {
 
 // One pixel's descriptor (K / 4 uint4 in registers) -> row r of K/4 swizzled atoms starting at `tile`.
 // Word wi of an atom fills the 16-byte chunks 2 wi (s = 0..3) and 2 wi + 1 (s = 4..7).
-template<int K, bool RIGHT>
+template<int K, bool RIGHT, bool CT = false>
 __device__ __forceinline__ void expand_pixel(const uint4 (&d)[K / 4], uint32_t tile, int r) {
     const uint32_t row = tile + (uint32_t)r * 128u;
     const uint32_t sw = (uint32_t)(r & 7);
@@ -282,7 +285,8 @@ __device__ __forceinline__ void expand_pixel(const uint4 (&d)[K / 4], uint32_t t
                 expand_word<RIGHT, 4>(w[wi]),
                 expand_word<RIGHT, 5>(w[wi]),
                 expand_word<RIGHT, 6>(w[wi]),
-                expand_word<RIGHT, 7>(w[wi])
+                // CT: the byte of the (unused, zero) top descriptor bit carries this row's tile column
+                (RIGHT && CT && q == K / 4 - 1 && wi == 3) ? (expand_word<RIGHT, 7>(w[wi]) | ((uint32_t)r << 24)) : expand_word<RIGHT, 7>(w[wi])
             );
         }
     }
@@ -315,39 +319,60 @@ struct TileMin16 {
     }
 };
 
+// CT ("column term"): the top descriptor bit (bit 32 K - 1) is unused in every descriptor the transform
+// writes (4n - 6 and n^2 - 2n + 3 are never a multiple of 32). Its byte in the left operand is therefore
+// always +1, and the producers put the tile column u into that byte of the right operand: the MMA itself
+// delivers acc + u, the first-minimum fold needs no addition and becomes a three-input minimum
+// (VIMNMX3[.S16x2]: two columns, or four packed ones, per instruction); the last-minimum key
+// acc + 127 - u is (acc + u) + (127 - 2u).
+
 // 32 accumulator columns starting at tile column U0
-template<bool NODUPES, int U0>
+template<bool NODUPES, int U0, bool CT>
 __device__ __forceinline__ void fold32(const int (&v)[32], TileMin32& m) {
+    if constexpr (CT) {
+#pragma unroll
+        for (int u = 0; u < 32; u += 2)
+            m.f[(u >> 1) & 3] = __vimin3_s32(m.f[(u >> 1) & 3], v[u], v[u + 1]);
+    }
 #pragma unroll
     for (int u = 0; u < 32; ++u) {
-        m.f[u & 3] = min(m.f[u & 3], v[u] + (U0 + u));
+        if constexpr (!CT)
+            m.f[u & 3] = min(m.f[u & 3], v[u] + (U0 + u));
         if constexpr (NODUPES)
-            m.l[u & 3] = min(m.l[u & 3], v[u] + (127 - U0 - u));
+            m.l[u & 3] = min(m.l[u & 3], v[u] + (CT ? 127 - 2 * (U0 + u) : 127 - U0 - u));
     }
 }
 
 // the same with a run-time bound: columns from `valid` on do not exist
-template<bool NODUPES>
+template<bool NODUPES, bool CT>
 __device__ __forceinline__ void fold32_guarded(const int (&v)[32], int u0, int valid, TileMin32& m) {
 #pragma unroll
     for (int u = 0; u < 32; ++u) {
         if (u0 + u < valid) {
-            m.f[u & 3] = min(m.f[u & 3], v[u] + (u0 + u));
+            m.f[u & 3] = min(m.f[u & 3], CT ? v[u] : v[u] + (u0 + u));
             if constexpr (NODUPES)
-                m.l[u & 3] = min(m.l[u & 3], v[u] + (127 - u0 - u));
+                m.l[u & 3] = min(m.l[u & 3], v[u] + (CT ? 127 - 2 * (u0 + u) : 127 - u0 - u));
         }
     }
 }
 
 // 64 accumulator columns starting at tile column U0, low halves packed two per register
-template<bool NODUPES, int U0>
+template<bool NODUPES, int U0, bool CT>
 __device__ __forceinline__ void fold64_packed(const int (&v)[32], TileMin16& m) {
+    if constexpr (CT) {
+#pragma unroll
+        for (int r = 0; r < 32; r += 2)
+            m.f[(r >> 1) & 7] = __vimin3_s16x2(m.f[(r >> 1) & 7], (uint32_t)v[r], (uint32_t)v[r + 1]);
+    }
 #pragma unroll
     for (int r = 0; r < 32; ++r) {
         constexpr uint32_t ONE = 0x00010001u;
         const uint32_t uf = (uint32_t)(U0 + 2 * r) * ONE + 0x00010000u; // columns U0 + 2r | U0 + 2r + 1
-        const uint32_t ul = (uint32_t)(127 - U0 - 2 * r) * ONE - 0x00010000u; // 127 - column
-        m.f[r & 7] = __viaddmin_s16x2((uint32_t)v[r], uf, m.f[r & 7]);
+        // 127 - column, or with the column already in the accumulator 127 - 2 column (16-bit lanes, two's complement)
+        const uint32_t ul = CT ? ((uint32_t)(uint16_t)(int16_t)(127 - 2 * (U0 + 2 * r + 1)) << 16) | (uint32_t)(uint16_t)(int16_t)(127 - 2 * (U0 + 2 * r))
+                               : (uint32_t)(127 - U0 - 2 * r) * ONE - 0x00010000u;
+        if constexpr (!CT)
+            m.f[r & 7] = __viaddmin_s16x2((uint32_t)v[r], uf, m.f[r & 7]);
         if constexpr (NODUPES)
             m.l[r & 7] = __viaddmin_s16x2((uint32_t)v[r], ul, m.l[r & 7]);
     }
@@ -422,7 +447,7 @@ struct Item {
     }
 };
 
-template<int K, bool NODUPES>
+template<int K, bool NODUPES, bool CT>
 __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(const MmaArgs p) {
     constexpr int KA = K / 4; // 128-bit atoms
     constexpr int NS = STAGES<K>;
@@ -568,7 +593,7 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
                 d[q] = ld_shared_v4(src + 16 * q);
             if (g >= NS)
                 mbar_wait(bar_stage_free + 8 * s, (g / NS - 1) & 1); // the MMAs that read this stage are done
-            expand_pixel<K, true>(d, s_b + (uint32_t)(s * KA * ATOM_BYTES), r);
+            expand_pixel<K, true, CT>(d, s_b + (uint32_t)(s * KA * ATOM_BYTES), r);
             // only now: the stores above consumed the loaded registers, so the packed slot has been read
             // (an arrive right after the loads was observed to let the next bulk copy overtake them)
             mbar_arrive(bar_packed_free + 8 * ps);
@@ -624,7 +649,7 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
                     for (int u0 = 0; u0 < TN && tile0 + u0 < cols; u0 += 32) {
                         tc_load32_issue(acc + (uint32_t)u0, va);
                         tc_load32_wait(va);
-                        fold32_guarded<NODUPES>(va, u0, cols - tile0, m);
+                        fold32_guarded<NODUPES, CT>(va, u0, cols - tile0, m);
                     }
                     tc_fence_before();
                     mbar_arrive(bar_acc_drained + 8 * a);
@@ -639,25 +664,25 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
                     tc_load32_wait(vb);
                     tc_fence_before();
                     mbar_arrive(bar_acc_drained + 8 * a);
-                    fold64_packed<NODUPES, 0>(va, m);
-                    fold64_packed<NODUPES, 64>(vb, m);
+                    fold64_packed<NODUPES, 0, CT>(va, m);
+                    fold64_packed<NODUPES, 64, CT>(vb, m);
                     merge_tile<NODUPES>(m, tile0, m_first, m_last);
                 } else {
                     TileMin32 m;
                     tc_load32_issue(acc, va);
                     tc_load32_wait(va);
                     tc_load32_issue(acc + 32, vb);
-                    fold32<NODUPES, 0>(va, m);
+                    fold32<NODUPES, 0, CT>(va, m);
                     tc_load32_wait(vb);
                     tc_load32_issue(acc + 64, va);
-                    fold32<NODUPES, 32>(vb, m);
+                    fold32<NODUPES, 32, CT>(vb, m);
                     tc_load32_wait(va);
                     tc_load32_issue(acc + 96, vb);
-                    fold32<NODUPES, 64>(va, m);
+                    fold32<NODUPES, 64, CT>(va, m);
                     tc_load32_wait(vb);
                     tc_fence_before();
                     mbar_arrive(bar_acc_drained + 8 * a);
-                    fold32<NODUPES, 96>(vb, m);
+                    fold32<NODUPES, 96, CT>(vb, m);
                     merge_tile<NODUPES>(m, tile0, m_first, m_last);
                 }
                 // The next item's left tile. With two buffers: early, the other buffer was last read by the
@@ -728,7 +753,7 @@ __device__ __forceinline__ void expand_left_to_tmem(const uint4 (&d)[K / 4], uin
     tc_store_wait();
 }
 
-template<int K, bool NODUPES>
+template<int K, bool NODUPES, bool CT>
 __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArgs p) {
     constexpr int KA = K / 4;
     constexpr int NS = V2_STAGES<K>;
@@ -873,7 +898,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
                 d[q] = ld_shared_v4(src + 16 * q);
             if (g >= NS)
                 mbar_wait(bar_stage_free + 8 * s, (g / NS - 1) & 1);
-            expand_pixel<K, true>(d, s_b + (uint32_t)(s * KA * ATOM_BYTES), r);
+            expand_pixel<K, true, CT>(d, s_b + (uint32_t)(s * KA * ATOM_BYTES), r);
             mbar_arrive(bar_packed_free + 8 * ps); // after the stores that consumed the loaded registers
             fence_async_smem();
             mbar_arrive(bar_stage_full + 8 * s);
@@ -927,7 +952,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
                     for (int u0 = 0; u0 < TN && tile0 + u0 < cols; u0 += 32) {
                         tc_load32_issue(acc + (uint32_t)u0, va);
                         tc_load32_wait(va);
-                        fold32_guarded<NODUPES>(va, u0, cols - tile0, m);
+                        fold32_guarded<NODUPES, CT>(va, u0, cols - tile0, m);
                     }
                     tc_fence_before();
                     mbar_arrive(bar_acc_drained + 8 * (2 * a + h));
@@ -940,25 +965,25 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
                     tc_load32_wait(vb);
                     tc_fence_before();
                     mbar_arrive(bar_acc_drained + 8 * (2 * a + h));
-                    fold64_packed<NODUPES, 0>(va, m);
-                    fold64_packed<NODUPES, 64>(vb, m);
+                    fold64_packed<NODUPES, 0, CT>(va, m);
+                    fold64_packed<NODUPES, 64, CT>(vb, m);
                     merge_tile<NODUPES>(m, tile0, m_first, m_last);
                 } else {
                     TileMin32 m;
                     tc_load32_issue(acc, va);
                     tc_load32_wait(va);
                     tc_load32_issue(acc + 32, vb);
-                    fold32<NODUPES, 0>(va, m);
+                    fold32<NODUPES, 0, CT>(va, m);
                     tc_load32_wait(vb);
                     tc_load32_issue(acc + 64, va);
-                    fold32<NODUPES, 32>(vb, m);
+                    fold32<NODUPES, 32, CT>(vb, m);
                     tc_load32_wait(va);
                     tc_load32_issue(acc + 96, vb);
-                    fold32<NODUPES, 64>(va, m);
+                    fold32<NODUPES, 64, CT>(va, m);
                     tc_load32_wait(vb);
                     tc_fence_before();
                     mbar_arrive(bar_acc_drained + 8 * (2 * a + h));
-                    fold32<NODUPES, 96>(vb, m);
+                    fold32<NODUPES, 96, CT>(vb, m);
                     merge_tile<NODUPES>(m, tile0, m_first, m_last);
                 }
                 // next item's left half: its TMEM columns are read only by this half's MMAs, all complete once
@@ -1033,10 +1058,10 @@ constexpr int v2_smem_bytes() {
     return V2_STAGES<K> * (K / 4) * ATOM_BYTES + V2_PACKED * TN * K * 4 + 1024;
 }
 
-template<int K, bool NODUPES>
+template<int K, bool NODUPES, bool CT>
 cudaError_t launch_k2(MmaArgs p, int dirs, cudaStream_t stream) {
     constexpr int smem = v2_smem_bytes<K>();
-    auto kernel = search_mma2_kernel<K, NODUPES>;
+    auto kernel = search_mma2_kernel<K, NODUPES, CT>;
     cudaError_t err = configure_once(kernel, smem);
     if (err != cudaSuccess)
         return err;
@@ -1050,10 +1075,10 @@ cudaError_t launch_k2(MmaArgs p, int dirs, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-template<int K, bool NODUPES>
+template<int K, bool NODUPES, bool CT>
 cudaError_t launch_k(MmaArgs p, int dirs, cudaStream_t stream) {
     const int smem = search_mma_smem_bytes(K);
-    auto kernel = search_mma_kernel<K, NODUPES>;
+    auto kernel = search_mma_kernel<K, NODUPES, CT>;
     cudaError_t err = configure_once(kernel, smem);
     if (err != cudaSuccess)
         return err;
@@ -1100,6 +1125,24 @@ void set_search_mma_variant(int v) {
     g_variant = v == 2 ? 2 : v == 1 ? 1 : 0;
 }
 
+namespace {
+int g_colterm = -1;
+}
+
+// Whether descriptors with a free top bit take the column-term kernels (fold32): environment
+// BICOS_B200_MMA_COLTERM = 0 | 1, default BICOS_MMA_COLTERM_DEFAULT.
+bool search_mma_colterm() {
+    if (g_colterm < 0) {
+        const char* v = getenv("BICOS_B200_MMA_COLTERM");
+        g_colterm = v ? (v[0] == '1') : BICOS_MMA_COLTERM_DEFAULT;
+    }
+    return g_colterm == 1;
+}
+
+void set_search_mma_colterm(bool on) {
+    g_colterm = on ? 1 : 0;
+}
+
 bool search_mma_supports(int K, int cols) {
     return (K == 4 || K == 8 || K == 12 || K == 16) && cols >= 1 && cols <= COL_MAX + 1;
 }
@@ -1116,7 +1159,8 @@ cudaError_t launch_search_mma(
     uint32_t* fwd_last,
     uint32_t* rev_first,
     uint32_t* rev_last,
-    cudaStream_t stream
+    cudaStream_t stream,
+    bool top_bit_free
 ) {
     if (rows <= 0 || !search_mma_supports(K, cols))
         return cudaErrorInvalidValue;
@@ -1139,20 +1183,26 @@ cudaError_t launch_search_mma(
     const long long pair_items = (long long)dirs * rows * ((cols + 2 * TM - 1) / (2 * TM));
     const int variant = search_mma_variant();
     const bool v2 = (K == 4 || K == 8) && (variant == 2 || (variant == 0 && pair_items >= 2 * sm_count_of_current_device()));
+    // column term through the MMA (see fold32): only where the caller vouches for the free top bit
+    const bool ct = top_bit_free && (K == 4 || K == 8) && search_mma_colterm();
+#define BICOS_MMA_DISPATCH(LAUNCH, KK)                                                                      \
+    (ct ? (nodupes ? LAUNCH<KK, true, true>(p, dirs, stream) : LAUNCH<KK, false, true>(p, dirs, stream))      \
+        : (nodupes ? LAUNCH<KK, true, false>(p, dirs, stream) : LAUNCH<KK, false, false>(p, dirs, stream)))
     if (v2 && K == 4)
-        return nodupes ? launch_k2<4, true>(p, dirs, stream) : launch_k2<4, false>(p, dirs, stream);
+        return BICOS_MMA_DISPATCH(launch_k2, 4);
     if (v2 && K == 8)
-        return nodupes ? launch_k2<8, true>(p, dirs, stream) : launch_k2<8, false>(p, dirs, stream);
+        return BICOS_MMA_DISPATCH(launch_k2, 8);
     switch (K) {
         case 4:
-            return nodupes ? launch_k<4, true>(p, dirs, stream) : launch_k<4, false>(p, dirs, stream);
+            return BICOS_MMA_DISPATCH(launch_k, 4);
         case 8:
-            return nodupes ? launch_k<8, true>(p, dirs, stream) : launch_k<8, false>(p, dirs, stream);
+            return BICOS_MMA_DISPATCH(launch_k, 8);
         case 12:
-            return nodupes ? launch_k<12, true>(p, dirs, stream) : launch_k<12, false>(p, dirs, stream);
+            return nodupes ? launch_k<12, true, false>(p, dirs, stream) : launch_k<12, false, false>(p, dirs, stream);
         case 16:
-            return nodupes ? launch_k<16, true>(p, dirs, stream) : launch_k<16, false>(p, dirs, stream);
+            return nodupes ? launch_k<16, true, false>(p, dirs, stream) : launch_k<16, false, false>(p, dirs, stream);
     }
+#undef BICOS_MMA_DISPATCH
     return cudaErrorInvalidValue;
 }
 

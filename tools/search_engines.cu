@@ -1,5 +1,5 @@
 // Parity and timing of the two search engines on the same descriptors:
-//   search_engines COLS ROWS K FLAGS [REPS] [POOL] [MMA_VARIANT]
+//   search_engines COLS ROWS K FLAGS [REPS] [POOL] [MMA_VARIANT] [COLTERM]
 // Descriptors are drawn from a small pool with a few flipped bits, so that exact ties (the
 // no-duplicates case) and near ties are frequent. The popcount engine (search.cu) is itself
 // pinned to the oracle by tests/test_gpu_parity.py; here the tensor-core engine (search_mma.cu)
@@ -32,6 +32,9 @@ int main(int argc, char** argv) {
     const int pool = argc > 6 ? std::atoi(argv[6]) : 64;
     if (argc > 7)
         set_search_mma_variant(std::atoi(argv[7])); // else: default / BICOS_B200_MMA_VARIANT
+    // COLTERM = 1: descriptors with a zero top bit (as the transform writes them) and the column-term kernels
+    const bool colterm = argc > 8 && std::atoi(argv[8]) != 0;
+    set_search_mma_colterm(colterm);
 
     const size_t pitch = ((size_t)cols * K + 3) / 4 * 4;
     std::mt19937 rng(1234u + cols + 7 * rows + 13 * K);
@@ -51,6 +54,8 @@ int main(int argc, char** argv) {
                     const int bit = rng() % (32 * K);
                     p[bit / 32] ^= 1u << (bit % 32);
                 }
+                if (colterm)
+                    p[K - 1] &= 0x7FFFFFFFu;
             }
     };
     std::vector<uint32_t> h0, h1;
@@ -75,7 +80,7 @@ int main(int argc, char** argv) {
         auto run = [&]() {
             return engine == 0
                 ? launch_search_popc(d0, d1, K, rows, cols, pitch, flags, k, k + px, k + 2 * px, k + 3 * px, 0)
-                : launch_search_mma(d0, d1, K, rows, cols, pitch, flags, k, k + px, k + 2 * px, k + 3 * px, 0);
+                : launch_search_mma(d0, d1, K, rows, cols, pitch, flags, k, k + px, k + 2 * px, k + 3 * px, 0, colterm);
         };
         CK(cudaMemset(k, 0xFF, px * 16));
         CK(run());
@@ -120,8 +125,8 @@ int main(int argc, char** argv) {
             ties += (a[i] & 0xFFFF) != 65535u - (a[px + i] & 0xFFFF);
     const double pairs = (double)rows * cols * cols * ((flags & FLAG_CONSISTENCY) ? 1 : 1);
     std::printf(
-        "cols %d rows %d K %d flags %d variant %d: popc %.4f ms (%.3f Tpair/s), mma %.4f ms (%.3f Tpair/s), speed-up %.2fx, forward ties %lld, %s\n",
-        cols, rows, K, flags, search_mma_variant(), ms[0], pairs / ms[0] * 1e-9, ms[1], pairs / ms[1] * 1e-9, ms[1] > 0 ? ms[0] / ms[1] : 0.0, ties,
+        "cols %d rows %d K %d flags %d variant %d colterm %d: popc %.4f ms (%.3f Tpair/s), mma %.4f ms (%.3f Tpair/s), speed-up %.2fx, forward ties %lld, %s\n",
+        cols, rows, K, flags, search_mma_variant(), (int)colterm, ms[0], pairs / ms[0] * 1e-9, ms[1], pairs / ms[1] * 1e-9, ms[1] > 0 ? ms[0] / ms[1] : 0.0, ties,
         bad_total ? "MISMATCH" : "identical"
     );
     return bad_total ? 1 : 0;
