@@ -91,3 +91,54 @@ def test_tile_keys_merge_to_first_and_last_minimum(cols):
     last = cols - 1 - (ham[:, ::-1] == best[:, None]).argmax(axis=1)
     assert np.array_equal(key_first, (best << 16) | first)
     assert np.array_equal(key_last, (best << 16) | (65535 - last))
+
+
+def _used_bits(n: int, full: bool) -> int:
+    """descriptor bits the transform can set (LIMITED 4n-6 for n >= 4, 4 and 7 bits for n = 2, 3)"""
+    if full:
+        return n * n - 2 * n + 3
+    return {2: 4, 3: 7}.get(n, 4 * n - 6)
+
+
+def test_top_descriptor_bit_is_never_used():
+    """What `top_bit_free` (bicos_b200_match -> launch_search) promises: for every stack size the reference accepts,
+    and for the wide-descriptor extension, the descriptor never fills its last word completely."""
+    import oracle
+
+    for full, sizes, wide in ((False, range(2, 66), False), (True, range(2, 17), False), (True, range(17, 24), True)):
+        for n in sizes:
+            k = oracle.words_per_descriptor(n, full, wide)
+            assert _used_bits(n, full) <= 32 * k - 1, (n, full, k)
+
+
+@pytest.mark.parametrize("n,dtype,full,wide", [(33, np.uint8, False, False), (65, np.uint8, False, False),
+                                               (12, np.uint8, True, False), (16, np.uint16, True, False),
+                                               (20, np.uint16, True, True)])
+def test_oracle_descriptors_leave_the_top_bit_clear(oracles, n, dtype, full, wide):
+    from libbicos_b200 import synth
+
+    left, right, _ = synth.make_stacks(n, 64, 96, dtype, seed=3 * n)
+    for stack in (left, right):
+        d = oracles.port.descriptors(stack, full, wide)
+        assert d.shape[-1] in (4, 8, 12, 16)
+        assert not (d[..., -1] >> 31).any()
+
+
+@pytest.mark.parametrize("k", [4, 8])
+def test_column_term_rides_in_the_top_bits_byte(k):
+    """With bit 32K-1 clear on both sides the left operand's byte for it is +1; putting the tile column u into that
+    byte of the right operand makes the GEMM deliver acc + u (fold32<CT> / fold64_packed<CT> in search_mma.cu)."""
+    rng = np.random.default_rng(100 + k)
+    left = rng.integers(0, 2**32, size=(64, k), dtype=np.uint64).astype(np.uint32)
+    right = rng.integers(0, 2**32, size=(TN, k), dtype=np.uint64).astype(np.uint32)
+    left[:, -1] &= 0x7FFFFFFF
+    right[:, -1] &= 0x7FFFFFFF
+    a, b = operands(left, True), operands(right, False)
+    top = 32 * k - 1  # k position of (last word, s = 7, byte 3) in the (word, s, byte) order
+    assert np.all(a[:, top] == 1) and np.all(b[:, top] == 0)
+    b[:, top] = np.arange(TN)  # what the producers OR in: the row's tile column, < 128, an unsigned byte
+    acc = a @ b.T
+    ham = popcount(left[:, None, :] ^ right[None, :, :])
+    assert np.array_equal(acc, 128 * (ham - popcount(left)[:, None]) + np.arange(TN)[None, :])
+    if k == 4:
+        assert np.abs(acc).max() + 127 < 2**15  # the last-minimum key adds 127 - 2u on top
