@@ -43,6 +43,14 @@ FRAMES = 4  # distinct stereo stacks per GPU per step (4 x 208 MB of input > 126
 CFG = dict(nxcorr_threshold=0.96, min_variance=2.0, subpixel_step=0.1, consistency=True, max_lr_diff=1)
 WORKLOAD = ("2x33 uint8 2048x1536, LIMITED, thr 0.96, min_var 2.0, subpixel_step 0.1, "
             "Consistency{max_lr_diff=1}, float")
+# one dictionary for both arms (the driver compares them): what is specific to an arm says so in its value
+CONFIG = {
+    "workload": WORKLOAD,
+    "frames_per_gpu_per_step": FRAMES,
+    "sharding": "frame-sharded, one process per GPU, no data-path collective",
+    "l2": f"inputs larger than L2 ({FRAMES} x 208 MB per GPU per step); no explicit flush",
+    "reference_arm_sample": "a bounded row sample of one stereo stack per step (cost is linear in rows), see cpu_baseline.sample",
+}
 
 
 def load_peaks():
@@ -161,8 +169,9 @@ def measure_int8_peak():
         return 2 * bf16, f"2 x the measured dense bf16 rate of MEASURED_PEAKS.json (torch._int_mm failed: {type(e).__name__})"
 
 
-def cpu_reference_run(rows, threads=None):
-    """Reference CPU backend on `rows` rows of frame 0 of the workload. Returns (seconds, kind, cores)."""
+def cpu_reference_run(rows, threads=None, keep=None):
+    """Reference CPU backend on `rows` rows of frame 0 of the workload. Returns (seconds, kind, cores).
+    `keep` (a dict) receives row0 and the reference's outputs, for the parity check of the bench line."""
     import numpy as np
 
     import oracle
@@ -176,8 +185,39 @@ def cpu_reference_run(rows, threads=None):
         lib.set_threads(threads)
     cores = threads or lib.hardware_threads()
     t0 = time.perf_counter()
-    lib.match(left, right, **CFG)
-    return time.perf_counter() - t0, kind, cores
+    disp, corr = lib.match(left, right, **CFG)
+    t = time.perf_counter() - t0
+    if keep is not None:
+        keep.update(row0=ROWS // 2 - rows // 2, rows=rows, disp=disp, corr=corr)
+    return t, kind, cores
+
+
+def parity_against_reference(keep, disp, corr, kind):
+    """The bench's own frame 0 (GPU, the kernels that were timed) against the reference CPU backend on the same
+    rows. north_star tolerances: valid mask bit-exact except where the NXC lies within 1e-6 of the threshold,
+    corrmap within 1e-5, subpixel disparity within 1e-3 px."""
+    import numpy as np
+
+    r0, rows = keep["row0"], keep["rows"]
+    gd, gc = disp[r0 : r0 + rows], corr[r0 : r0 + rows]
+    wd, wc = keep["disp"], keep["corr"]
+    inv_g, inv_w = np.isnan(gd), np.isnan(wd)
+    edge = np.abs(np.nan_to_num(wc, nan=9.0) - CFG["nxcorr_threshold"]) < 1e-6
+    mask_mismatch = int(((inv_g != inv_w) & ~edge).sum())
+    both = ~(inv_g | inv_w)
+    okc = ~np.isnan(wc) & ~np.isnan(gc)
+    out = {
+        "against": f"oracle/{'_ref (unmodified reference CPU backend)' if kind == 'reference' else 'port'}",
+        "frame": 0, "row0": r0, "rows": rows, "pixels": int(gd.size), "valid": int(both.sum()),
+        "mask_mismatch": mask_mismatch, "threshold_edge_pixels": int(edge.sum()),
+        "corr_nan_mismatch": int((np.isnan(gc) != np.isnan(wc)).sum()),
+        "disp_max_abs": float(np.max(np.abs(gd[both] - wd[both]), initial=0.0)),
+        "corr_max_abs": float(np.max(np.abs(gc[okc] - wc[okc]), initial=0.0)),
+        "bit_identical": bool(np.array_equal(gd, wd, equal_nan=True) and np.array_equal(gc, wc, equal_nan=True)),
+    }
+    out["within_north_star"] = bool(out["mask_mismatch"] == 0 and out["corr_nan_mismatch"] == 0
+                                    and out["disp_max_abs"] <= 1e-3 and out["corr_max_abs"] <= 1e-5)
+    return out
 
 
 def run_reference_arm(args):
@@ -200,7 +240,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "Mpx/s disparity", "value": value, "unit": "Mpx/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": CONFIG,
         "cpu_baseline": {"value": value, "unit": "Mpx/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -295,8 +335,11 @@ def main():
     total_ms = max_over_ranks(ev0.elapsed_time(ev1))
     stage_ms, n_matches = h.stage_times()
     h.set_profiling(False)
+    search_kernel = lb.last_search_kernel()  # what the timed matches dispatched, e.g. mma2<K=4,nodupes=0,ct=1,dirs=2>
     launches = h.kernel_launches - launches0
     clocks = sampler.stop() if rank == 0 else None
+    # frame 0 as the timed region left it (the engine comparison further down writes into `outs` again)
+    timed_frame0 = (outs[0][0].cpu().numpy(), outs[0][1].cpu().numpy()) if rank == 0 else None
     ms_per_step = total_ms / args.steps
     value = world * FRAMES * px / (ms_per_step * 1e-3) / 1e6
 
@@ -330,6 +373,49 @@ def main():
     barrier()
     e2e_value = world * FRAMES * px / (e2e_ms * 1e-3) / 1e6
     same = bool(np.array_equal(host_out[0][0], outs[0][0].cpu().numpy(), equal_nan=True))
+
+    # ---- N > 1: ONE match of the same workload row-sharded over the N GPUs (strong scaling; BASELINE.json
+    #      configs[2] / [3] ask for this mode). Rank g holds rows [g H / N, (g + 1) H / N) of frame 0 and runs the
+    #      whole path on them; the refine kernels store their rows into rank 0's images over NVLink peer memory
+    #      (sharding.PeerAssembly), so the only exchange is that store. Device time = max over ranks. ----
+    row_sharded = None
+    if world > 1:
+        from libbicos_b200 import sharding
+
+        lo, hi = sharding.row_range(rank, world, ROWS)
+        sl, sr = synth.make_stacks(N_IMAGES, ROWS, COLS, np.uint8, row0=lo, rows=hi - lo, xp=torch, device="cuda")[:2]
+        pa = sharding.PeerAssembly(h, ROWS, COLS, cfg, local)
+        for _ in range(3):
+            pa.match(sl, sr)
+            pa.finish()
+        ts = []
+        for _ in range(20):
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            pa.match(sl, sr)
+            b.record()
+            pd, pc = pa.finish()
+            ts.append(max_over_ranks(a.elapsed_time(b)))
+        shard_kernel = lb.last_search_kernel()
+        if rank == 0:
+            single = []
+            l0, r0 = frames[0]
+            for _ in range(5):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                h.match(l0, r0, cfg, out=outs[0])
+                b.record()
+                torch.cuda.synchronize()
+                single.append(a.elapsed_time(b))
+            single_ms, shard_ms = float(np.median(single)), float(np.median(ts))
+            eq = bool(torch.equal(torch.nan_to_num(pd, nan=-7.0), torch.nan_to_num(outs[0][0], nan=-7.0))
+                      and torch.equal(torch.nan_to_num(pc, nan=-7.0), torch.nan_to_num(outs[0][1], nan=-7.0)))
+            row_sharded = {"ms_per_match": shard_ms, "ms_per_match_min": float(np.min(ts)), "mpx_per_s": px / shard_ms / 1e3,
+                           "single_gpu_ms_per_match": single_ms, "speedup_vs_1gpu": single_ms / shard_ms,
+                           "rows_per_gpu": hi - lo, "assembly": "peer", "search_kernel_per_shard": shard_kernel,
+                           "equals_single_gpu": eq, "scaling": "strong"}
+        pa.close()
 
     if rank != 0:
         if world > 1:
@@ -366,7 +452,7 @@ def main():
 
     popc_issued = COLS * px * 3  # the popc kernel's carry-save form: 3 POPC per 128-bit pair
     popc_line = {
-        "kernel": "search_kernel<4, CONSISTENCY>", "bound": "popc", "achieved": popc_alg / t_popc / 1e12,
+        "kernel": "search_kernel<K=4, CONSISTENCY> (popc engine)", "bound": "popc", "achieved": popc_alg / t_popc / 1e12,
         "peak": popc_peak / 1e12, "unit": "Tpopc32/s", "frac": popc_alg / t_popc / popc_peak,
         "pipe_frac": popc_issued / t_popc / popc_peak, "traffic": traffic.get("search"),
         "peak_source": popc_src, "ms_per_launch": t_popc * 1e3,
@@ -375,21 +461,28 @@ def main():
     }
     int8_peak, int8_src = measure_int8_peak()
     dirs = 2  # Consistency: forward and reverse search, each a full W x W x 128 product per row
-    mma_ops = 2.0 * COLS * px * 32 * K * dirs
+    # SURVEY 8d scores every left/right descriptor pair of a row ONCE, however often an implementation visits it:
+    # `frac` is that algorithmic figure, `frac_executed` counts what the kernel issues (both directions)
+    mma_ops_once = 2.0 * COLS * px * 32 * K
+    mma_ops = mma_ops_once * dirs
     smem_bytes = (COLS / 128) * (px / 128) * dirs * 26 * 1024  # variant 2, per 128x128 tile: 16 KB operand reads, 8 KB expansion, 2 KB packed ring
     mma_line = {
-        "kernel": "search_mma2_kernel<4, CONSISTENCY>", "bound": "tensor", "achieved": mma_ops / t_mma / 1e12,
-        "peak": int8_peak, "unit": "TOP/s", "frac": mma_ops / t_mma / 1e12 / int8_peak, "traffic": traffic.get("search_mma"),
-        "peak_source": int8_src, "ms_per_launch": t_mma * 1e3,
+        "kernel": search_kernel, "bound": "tensor", "achieved": mma_ops_once / t_mma / 1e12,
+        "peak": int8_peak, "unit": "TOP/s", "frac": mma_ops_once / t_mma / 1e12 / int8_peak, "traffic": traffic.get("search_mma2"),
+        "peak_kind": "dense int8 tensor rate (tcgen05 kind::i8)", "peak_source": int8_src, "ms_per_launch": t_mma * 1e3,
+        "achieved_executed": mma_ops / t_mma / 1e12, "frac_executed": mma_ops / t_mma / 1e12 / int8_peak,
+        "executed_over_algorithmic": dirs,
         "smem_frac": smem_bytes / t_mma / (128.0 * 148 * sm_max * 1e6),
         # SURVEY 8d scores the search in popc32 (S = W * P * K) against the POPC pipe, the bound of a popcount kernel:
         # the same algorithmic work over this engine's time, for comparison with that table
         "algorithmic_popc32": {"achieved": popc_alg / t_mma / 1e12, "peak": popc_peak / 1e12, "unit": "Tpopc32/s",
                                "frac": popc_alg / t_mma / popc_peak, "peak_source": popc_src},
-        "note": "the tensor-core engine (default): W x W x 128-bit Hamming matrix per row and direction as int8 tcgen05.mma "
-                "(kind::i8, TMEM accumulators), argmin in the epilogue; achieved = 2*W*P*bits*directions int8 ops per "
-                "launch over the stage time. smem_frac: shared-memory bytes the kernel moves (streamed-operand reads of the MMAs, "
-                "the resident operand lives in TMEM, + operand expansion) over 128 B/clk/SM",
+        "note": "the tensor-core engine (default): W x W x 128-bit Hamming matrix per row as int8 tcgen05.mma (kind::i8, TMEM "
+                "accumulators), argmin in the epilogue. frac = 2*W*P*bits int8 ops (every descriptor pair once, SURVEY 8d) over "
+                "the stage time and the dense int8 rate; frac_executed counts both directions of the consistency check, which "
+                "this kernel computes as two products (column-wise minima of one product cost more instructions than the "
+                "second product: profiles/r02_ncu_search_mma_history.md). smem_frac: shared-memory bytes the kernel moves "
+                "(streamed-operand reads of the MMAs, the resident operand lives in TMEM, + operand expansion) over 128 B/clk/SM",
     }
     roofline = mma_line if tensor else popc_line
     roofline["engine"] = "tensor" if tensor else "popc"
@@ -405,13 +498,20 @@ def main():
     ]
 
     cpu_baseline = None
+    parity = None
     if world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)  # the CPU reference gets every host core again
         t, kind, cores = cpu_reference_run(16)
-        rows = int(min(ROWS, max(16, 16 * (12.0 / max(t, 1e-3)))))  # about 10-15 s of CPU work
-        t, kind, cores = cpu_reference_run(rows)
+        # the whole frame when that stays under a minute (16 host cores: about 6 s), else about 15 s of CPU work
+        est = t / 16 * ROWS
+        rows = ROWS if est <= 60.0 else int(min(ROWS, max(16, 16 * (15.0 / max(t, 1e-3)))))
+        keep = {}
+        t, kind, cores = cpu_reference_run(rows, keep=keep)
         cpu_baseline = {"value": rows * COLS / t / 1e6, "unit": "Mpx/s", "cores": cores, "kind": kind,
                         "sample": f"{rows} of {ROWS} rows of one stereo stack, {t:.1f} s wall, all host threads"}
+        # the frame the timed region produced last (same kernels, same dispatch) against the reference's output
+        parity = parity_against_reference(keep, timed_frame0[0], timed_frame0[1], kind)
+        parity["search_kernel"] = search_kernel
 
     # the reference's own CUDA backend, unmodified, compiled for sm_100a (oracle/_ref/libbicos_refcuda.so):
     # a second baseline beside the CPU build (BASELINE.json north_star); device-resident inputs
@@ -433,16 +533,19 @@ def main():
         "metric": "Mpx/s disparity", "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "ms_per_match": ms_per_step / FRAMES,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": FRAMES, "sharding": f"frame-sharded x{world}",
-                   "l2": f"inputs larger than L2 ({FRAMES} x 208 MB per step per GPU); no explicit flush"},
+        "config": CONFIG,
         "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": FRAMES * 2 * N_IMAGES * px,
                 "d2h_bytes_per_step": FRAMES * px * 8, "ms_per_step": e2e_ms, "matches_device_path": same, "host_affinity": affinity,
                 "api": f"bicos_b200_match_host_begin/_end, {inflight} frames in flight (pinned host stacks -> host disparity + corrmap)"},
         "gpu_launches": launches,
         "stage_ms_per_match": {"transform_x2": t_tr * 1e3, "search": t_se * 1e3, "refine": t_re * 1e3},
-        "roofline": roofline, "roofline_other": roofline_other, "cpu_baseline": cpu_baseline, "reference_cuda": reference_cuda, "clocks": clocks,
+        "roofline": roofline, "roofline_other": roofline_other, "cpu_baseline": cpu_baseline, "parity": parity,
+        "row_sharded": row_sharded, "reference_cuda": reference_cuda, "clocks": clocks,
     }
     print(json.dumps(line))
+    if parity is not None and not parity["within_north_star"]:
+        print(f"bench.py: PARITY FAILURE against the reference: {parity}", file=sys.stderr)
+        sys.exit(3)
     if world > 1:
         dist.destroy_process_group()
 

@@ -10,7 +10,12 @@
 //    (src/impl/cpu.cpp:77-95), which is the parity oracle of this implementation.
 //  * corrmap: only touched when cfg.nxcorr_threshold is set; float32 (SINGLE) or float64
 //    (DOUBLE), NaN where no correlation was evaluated.
-//  * stream: a cudaStream_t (nullptr = default stream). Work is enqueued, not synchronised.
+//  * stream: a cudaStream_t (nullptr = default stream); with -DBICOS_WITH_OPENCV a cv::cuda::Stream&, exactly
+//    the reference's signature. Work is enqueued, not synchronised. Matches issued by one host thread on one
+//    device share a workspace (descriptors, search keys): a match enqueued on another stream than the
+//    thread's previous one first waits, on the device, for that previous match (the reference allocates per
+//    call instead and so never overlaps either: its destructors synchronise, src/impl/cuda.cu:79-94). For
+//    matches that really run side by side use one host thread per stream.
 //
 // Errors: BICOS::Exception for n < 2, bad depths and CUDA failures; std::invalid_argument
 // when the stack needs more than 256 descriptor bits -- as in the reference
@@ -24,8 +29,36 @@
 
 #include <vector>
 
+#ifdef BICOS_WITH_OPENCV
+    #include <opencv2/core/cuda.hpp>
+    #include <opencv2/core/cuda_stream_accessor.hpp>
+#endif
+
 namespace BICOS {
 
+#ifdef BICOS_WITH_OPENCV
+// raw-stream form; the defaulted sixth parameter belongs to the cv::cuda::Stream overload below
+void match(
+    const std::vector<Image>& stack0,
+    const std::vector<Image>& stack1,
+    Image& disparity,
+    Config cfg,
+    Image* corrmap,
+    void* stream
+);
+
+// the reference's signature (include/match.hpp:31-41)
+inline void match(
+    const std::vector<Image>& stack0,
+    const std::vector<Image>& stack1,
+    Image& disparity,
+    Config cfg = Config {},
+    Image* corrmap = nullptr,
+    cv::cuda::Stream& stream = cv::cuda::Stream::Null()
+) {
+    match(stack0, stack1, disparity, cfg, corrmap, static_cast<void*>(cv::cuda::StreamAccessor::getStream(stream)));
+}
+#else
 void match(
     const std::vector<Image>& stack0,
     const std::vector<Image>& stack1,
@@ -34,6 +67,7 @@ void match(
     Image* corrmap = nullptr,
     void* stream = nullptr
 );
+#endif
 
 // Row-sharded match over several GPUs of one node from a single process: device g handles
 // rows [g*H/G, (g+1)*H/G) and writes its rows of `disparity` / `corrmap` (allocated on

@@ -46,6 +46,11 @@ typedef enum {
 /* reference include/impl/common.hpp:46-47 */
 #define BICOS_B200_FLAG_NODUPES 1
 #define BICOS_B200_FLAG_CONSISTENCY 2
+/* bicos_b200_search only, OR-ed into `flags`: the caller vouches that bit 32 K - 1 of every descriptor is zero
+ * (true for everything bicos_b200_transform writes: 4n-6 and n^2-2n+3 are never multiples of 32). The
+ * tensor-core engine then carries the tile column through that bit's operand byte (search_mma.cu, "CT"),
+ * as bicos_b200_match does; a set top bit with this flag gives wrong matches. */
+#define BICOS_B200_FLAG_TOP_BIT_FREE 4
 
 /* Same fields, order and "negative float = unset" convention as the reference's BicosConfig
  * (src/pybicos_c.cpp:30-41 with BICOS_CUDA defined; pybicos/__init__.py:41-51), plus one
@@ -205,6 +210,11 @@ long long bicos_b200_kernel_launches(bicos_b200_handle h);
 enum { BICOS_B200_SEARCH_AUTO = 0, BICOS_B200_SEARCH_POPC = 1, BICOS_B200_SEARCH_TENSOR = 2 };
 int bicos_b200_set_search_engine(int engine);
 int bicos_b200_get_search_engine(void);
+
+/* Name of the kernel the calling thread's last search dispatched, e.g. "mma2<K=4,nodupes=0,ct=1,dirs=2>",
+ * "mma1<...>" or "popc<K=4,flags=2>"; "" before the first search. For tests and benchmarks that must know
+ * which of the engine's kernels they exercised. The string is thread-local and valid until the next search. */
+const char* bicos_b200_last_search_kernel(void);
 
 #ifdef __cplusplus
 }

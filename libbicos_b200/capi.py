@@ -16,7 +16,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libbicos_b200.so")
 
 DEPTH_8U, DEPTH_16U, TYPE_16S, TYPE_32F, TYPE_64F = 0, 2, 3, 5, 6
-FLAG_NODUPES, FLAG_CONSISTENCY = 1, 2
+FLAG_NODUPES, FLAG_CONSISTENCY, FLAG_TOP_BIT_FREE = 1, 2, 4
 MAX_IMAGES = 65
 
 EXPORTS = (
@@ -26,7 +26,7 @@ EXPORTS = (
     "bicos_b200_match_host", "bicos_b200_match_host_begin", "bicos_b200_match_host_end", "bicos_b200_match_rows", "bicos_b200_synchronize",
     "bicos_b200_kernel_launches", "bicos_b200_set_profiling", "bicos_b200_stage_times",
     "bicos_b200_shared_alloc", "bicos_b200_shared_open", "bicos_b200_shared_close", "bicos_b200_shared_free",
-    "bicos_b200_set_search_engine", "bicos_b200_get_search_engine",
+    "bicos_b200_set_search_engine", "bicos_b200_get_search_engine", "bicos_b200_last_search_kernel",
 )
 SEARCH_ENGINES = {"auto": 0, "popc": 1, "tensor": 2}
 IPC_HANDLE_BYTES = 64
@@ -99,6 +99,8 @@ def lib():
         L.bicos_b200_last_error.restype = ctypes.c_char_p
         L.bicos_b200_set_search_engine.argtypes = [ctypes.c_int]
         L.bicos_b200_get_search_engine.argtypes = []
+        L.bicos_b200_last_search_kernel.restype = ctypes.c_char_p
+        L.bicos_b200_last_search_kernel.argtypes = []
         L.bicos_b200_kernel_launches.restype = ctypes.c_longlong
         L.bicos_b200_kernel_launches.argtypes = [ctypes.c_void_p]
         vp, i, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
@@ -150,6 +152,11 @@ def set_search_engine(engine: str) -> None:
 def search_engine() -> str:
     code = lib().bicos_b200_get_search_engine()
     return next(k for k, v in SEARCH_ENGINES.items() if v == code)
+
+
+def last_search_kernel() -> str:
+    """Which kernel this thread's last search dispatched, e.g. 'mma2<K=4,nodupes=0,ct=1,dirs=2>' or 'popc<K=4,flags=2>'."""
+    return lib().bicos_b200_last_search_kernel().decode()
 
 
 def _ptr_array(ptrs: Sequence[int]):
@@ -222,11 +229,13 @@ class Handle:
                                           desc.data_ptr(), pitch_words, self._stream()))
         return desc, k
 
-    def search(self, desc0, desc1, k: int, cols: int, flags: int):
+    def search(self, desc0, desc1, k: int, cols: int, flags: int, top_bit_free: bool = False):
         """Row-wise search on pitched descriptors -> (fwd_first, fwd_last, rev_first, rev_last).
 
         Each is a [rows, cols] int32 tensor holding uint32 keys cost << 16 | column (see
-        include/bicos_b200.h), or None when `flags` does not need it."""
+        include/bicos_b200.h), or None when `flags` does not need it. ``top_bit_free``: the caller
+        vouches that bit 32k-1 of every descriptor is zero (BICOS_B200_FLAG_TOP_BIT_FREE; true for
+        transform() output), which lets the tensor-core engine use its column-term kernels."""
         import torch
 
         rows, pitch_words = desc0.shape
@@ -241,7 +250,7 @@ class Handle:
         revl = keys(flags == (FLAG_NODUPES | FLAG_CONSISTENCY))
         ptr = [t.data_ptr() if t is not None else None for t in (fwdf, fwdl, revf, revl)]
         _check(lib().bicos_b200_search(self._h, desc0.data_ptr(), desc1.data_ptr(), k, rows, cols, pitch_words,
-                                       flags, *ptr, self._stream()))
+                                       flags | (FLAG_TOP_BIT_FREE if top_bit_free else 0), *ptr, self._stream()))
         return fwdf, fwdl, revf, revl
 
     def _outputs(self, cfg: Config, rows: int, cols: int, device):
@@ -275,6 +284,51 @@ class Handle:
             corr.stride(0) * corr.element_size() if corr is not None else 0, self._stream()))
         return disp, corr, raw
 
+    @staticmethod
+    def _check_out(ccfg, out, rows: int, cols: int, device=None):
+        """Caller-supplied (disparity, corrmap) buffers must have the types bicos_b200_disparity_type /
+        _corrmap_type name for this configuration, shape (rows, cols) and unit inner stride: the kernels and
+        the D2H copies write rows * cols elements of that type without looking at the buffer again.
+        `device` = a torch device for the device-resident entry points, None for host (numpy) buffers,
+        which must also be C-contiguous (they are filled by flat copies)."""
+        import numpy as np
+
+        dt = lib().bicos_b200_disparity_type(ctypes.byref(ccfg))
+        ct = lib().bicos_b200_corrmap_type(ctypes.byref(ccfg))
+        try:
+            disp, corr = out
+        except (TypeError, ValueError):
+            raise BicosError("out must be a (disparity, corrmap) pair") from None
+        want_np = {TYPE_16S: np.int16, TYPE_32F: np.float32, TYPE_64F: np.float64}
+
+        def check(buf, code, what):
+            if device is not None:
+                import torch
+
+                want = {TYPE_16S: torch.int16, TYPE_32F: torch.float32, TYPE_64F: torch.float64}[code]
+                if not isinstance(buf, torch.Tensor) or buf.dtype != want:
+                    raise BicosError(f"out {what} must be a {want} tensor for this configuration")
+                if buf.device != device:
+                    raise BicosError(f"out {what} lives on {buf.device}, the stacks on {device}")
+                if tuple(buf.shape) != (rows, cols) or buf.stride(1) != 1 or buf.stride(0) < cols:
+                    raise BicosError(f"out {what} must have shape ({rows}, {cols}) with contiguous rows")
+            else:
+                if not isinstance(buf, np.ndarray) or buf.dtype != want_np[code]:
+                    raise BicosError(f"out {what} must be a {np.dtype(want_np[code]).name} array for this configuration")
+                if buf.shape != (rows, cols) or not buf.flags.c_contiguous or not buf.flags.writeable:
+                    raise BicosError(f"out {what} must be a writable C-contiguous array of shape ({rows}, {cols})")
+
+        if disp is None:
+            raise BicosError("out disparity is None")
+        check(disp, dt, "disparity")
+        if ct:
+            if corr is None:
+                raise BicosError("this configuration has a threshold: out needs a corrmap buffer")
+            check(corr, ct, "corrmap")
+        elif corr is not None:
+            raise BicosError("this configuration has no threshold: out corrmap must be None")
+        return disp, corr
+
     # ---- whole path ---------------------------------------------------------------------
     def match(self, stack0, stack1, cfg: Config, out=None, rows_range=None):
         """Device-resident BICOS::match on [n, rows, cols] uint8/uint16 CUDA tensors.
@@ -290,7 +344,7 @@ class Handle:
             ccfg, disp, corr = self._outputs(cfg, rows, cols, stack0.device)
         else:
             ccfg = cfg.to_c()
-            disp, corr = out
+            disp, corr = self._check_out(ccfg, out, rows, cols, stack0.device)
         args = [disp.data_ptr(), disp.stride(0) * disp.element_size(),
                 corr.data_ptr() if corr is not None else None,
                 corr.stride(0) * corr.element_size() if corr is not None else 0, self._stream()]
@@ -352,7 +406,11 @@ class Handle:
             disp = np.empty((rows, cols), dtype=np.int16 if dt == TYPE_16S else np.float32)
             corr = np.empty((rows, cols), dtype=np.float64 if ct == TYPE_64F else np.float32) if ct else None
         else:
-            disp, corr = (as_np(o) if o is not None else None for o in out)
+            try:
+                out = tuple(as_np(o) if o is not None else None for o in out)
+            except TypeError:
+                raise BicosError("out must be a (disparity, corrmap) pair") from None
+            disp, corr = self._check_out(ccfg, out, rows, cols)
         _check(lib().bicos_b200_match_host_begin(
             self._h, _ptr_array([p.ctypes.data for p in planes0]), _ptr_array([p.ctypes.data for p in planes1]),
             n, rows, cols, depth, ctypes.byref(ccfg), disp.ctypes.data,

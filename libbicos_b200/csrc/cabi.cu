@@ -10,6 +10,8 @@
 #include "../../include/bicos_b200.h"
 #include "kernels.cuh"
 
+#include <nvtx3/nvToolsExt.h> // header-only; a no-op unless a profiler injects itself
+
 #include <cmath>
 #include <condition_variable>
 #include <cstdarg>
@@ -43,12 +45,33 @@ int cuda_fail(cudaError_t err, const char* what) {
     return fail(BICOS_B200_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(err), cudaGetErrorName(err));
 }
 
+// a tensor-core search kernel gave up on a wait since the last check (search_mma.cu, mbar_wait_slow)
+int check_search_timeout() {
+    if (const unsigned int v = search_mma_take_timeout())
+        return fail(BICOS_B200_ERR_CUDA,
+                    "search pipeline timeout (CTA %u): a wait inside the tensor-core search kernel exceeded BICOS_B200_MMA_TIMEOUT_MS; "
+                    "results of that match are invalid (BICOS_B200_SEARCH_ENGINE=popc selects the other engine)", v - 1);
+    return 0;
+}
+
 #define CU(call) \
     do { \
         cudaError_t err__ = (call); \
         if (err__ != cudaSuccess) \
             return cuda_fail(err__, #call); \
     } while (0)
+
+// NVTX range around a host-side section (stage launches, host staging): shows up on the ncu / nsys timeline
+struct Range {
+    explicit Range(const char* name) {
+        nvtxRangePushA(name);
+    }
+    ~Range() {
+        nvtxRangePop();
+    }
+    Range(const Range&) = delete;
+    Range& operator=(const Range&) = delete;
+};
 
 struct DeviceBuffer {
     void* ptr = nullptr;
@@ -270,6 +293,11 @@ struct bicos_b200_handle_s {
     void *user_disp = nullptr, *user_corr = nullptr; // where _end copies the pinned outputs to
     size_t user_disp_bytes = 0, user_corr_bytes = 0;
     long long launches = 0;
+    // the workspace (descriptors, keys, x table) is shared by all matches of the handle: a match enqueued on
+    // another stream than the previous one first waits for it (do_match)
+    cudaEvent_t ev_last = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool has_last = false;
     // host-buffer pipeline (bicos_b200_match_host): upload / compute / download streams
     cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[MAX_BANDS] = {}, ev_done[MAX_BANDS] = {};
@@ -484,6 +512,7 @@ int do_match(
     if (pitch_bytes < (size_t)cols * depth_bytes(depth))
         return fail(BICOS_B200_ERR_INVALID, "pitch smaller than a row");
 
+    Range nvtx_match("bicos_b200::match");
     const int nrows = row_end - row_begin;
     PlaneTable t0, t1;
     if (int rc = fill_table(t0, planes0, n, (size_t)row_begin * pitch_bytes))
@@ -491,9 +520,13 @@ int do_match(
     if (int rc = fill_table(t1, planes1, n, (size_t)row_begin * pitch_bytes))
         return rc;
 
+    if (int rc = check_search_timeout())
+        return rc;
     const int flags = search_flags(cfg);
     const size_t dpw = desc_pitch_for(cols, K);
     const size_t px = (size_t)nrows * cols;
+    if (h->has_last && h->last_stream != stream)
+        CU(cudaStreamWaitEvent(stream, h->ev_last, 0)); // the previous match still owns the workspace
     CU(h->desc0.reserve(dpw * nrows * sizeof(uint32_t)));
     CU(h->desc1.reserve(dpw * nrows * sizeof(uint32_t)));
     // key arrays, contiguous so that one memset initialises them: fwd_first, then fwd_last
@@ -506,25 +539,38 @@ int do_match(
     const int is_u16 = depth == BICOS_B200_16U;
     if (int rc = prof_mark(h, stream))
         return rc;
-    CU(launch_transform(t0, n, nrows, cols, pitch_bytes, is_u16, mode_is_full(cfg->mode), K, d0, dpw, stream));
-    CU(launch_transform(t1, n, nrows, cols, pitch_bytes, is_u16, mode_is_full(cfg->mode), K, d1, dpw, stream));
-    h->launches += 2;
+    {
+        Range nvtx("bicos_b200::transform x2");
+        CU(launch_transform(t0, n, nrows, cols, pitch_bytes, is_u16, mode_is_full(cfg->mode), K, d0, dpw, stream));
+        CU(launch_transform(t1, n, nrows, cols, pitch_bytes, is_u16, mode_is_full(cfg->mode), K, d1, dpw, stream));
+        h->launches += 2;
+    }
     if (int rc = prof_mark(h, stream))
         return rc;
 
     KeyArrays ka = split_keys(static_cast<uint32_t*>(h->keys.ptr), px, flags);
-    CU(cudaMemsetAsync(h->keys.ptr, 0xFF, px * sizeof(uint32_t) * n_keys, stream));
+    if (search_needs_prefill(K, cols)) // the popcount engine merges with atomicMin; the tensor-core engine stores every key
+        CU(cudaMemsetAsync(h->keys.ptr, 0xFF, px * sizeof(uint32_t) * n_keys, stream));
     // descriptors of our own transform: 4n - 6 or n^2 - 2n + 3 bits, never all 32 K, so the top bit is free
-    CU(launch_search(d0, d1, K, nrows, cols, dpw, flags, ka.fwd_first, ka.fwd_last, ka.rev_first, ka.rev_last, stream, true));
-    h->launches += 1;
+    {
+        Range nvtx("bicos_b200::search");
+        CU(launch_search(d0, d1, K, nrows, cols, dpw, flags, ka.fwd_first, ka.fwd_last, ka.rev_first, ka.rev_last, stream, true));
+        h->launches += 1;
+    }
     if (int rc = prof_mark(h, stream))
         return rc;
 
     char* disp_rows = static_cast<char*>(disparity) + (size_t)row_begin * disparity_pitch;
     char* corr_rows = corrmap ? static_cast<char*>(corrmap) + (size_t)row_begin * corrmap_pitch : nullptr;
+    Range nvtx_refine("bicos_b200::postfilter+refine");
     if (int rc = do_refine(h, t0, t1, n, nrows, cols, pitch_bytes, depth, cfg, ka.fwd_first, ka.fwd_last, ka.rev_first, ka.rev_last,
                            nullptr, disp_rows, disparity_pitch, corr_rows, corrmap_pitch, stream))
         return rc;
+    if (!h->ev_last)
+        CU(cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming));
+    CU(cudaEventRecord(h->ev_last, stream));
+    h->last_stream = stream;
+    h->has_last = true;
     return prof_mark(h, stream);
 }
 
@@ -578,6 +624,8 @@ int bicos_b200_destroy(bicos_b200_handle h) {
             b->release();
         for (cudaEvent_t e: h->prof_events)
             cudaEventDestroy(e);
+        if (h->ev_last)
+            cudaEventDestroy(h->ev_last);
         for (int k = 0; k < PIN_SLOTS; ++k) {
             h->pin_in[k].release();
             if (h->ev_slot[k])
@@ -648,8 +696,10 @@ int bicos_b200_search(bicos_b200_handle h, const uint32_t* desc0, const uint32_t
         return fail(BICOS_B200_ERR_INVALID, "null argument");
     if (K != 1 && K != 2 && K != 4 && K != 8 && K != 12 && K != 16)
         return fail(BICOS_B200_ERR_INVALID, "K must be 1, 2, 4 or 8 (12 or 16 for wide descriptors)");
-    if (flags < 0 || flags > 3)
+    if (flags < 0 || flags > 7)
         return fail(BICOS_B200_ERR_INVALID, "bad flags");
+    const bool top_bit_free = (flags & BICOS_B200_FLAG_TOP_BIT_FREE) != 0;
+    flags &= 3;
     if (rows <= 0 || cols <= 0 || cols > 32767)
         return fail(BICOS_B200_ERR_INVALID, "bad image size");
     if ((flags & FLAG_NODUPES) && !fwd_last)
@@ -661,15 +711,17 @@ int bicos_b200_search(bicos_b200_handle h, const uint32_t* desc0, const uint32_t
     DeviceGuard g(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t bytes = (size_t)rows * cols * sizeof(uint32_t);
-    CU(cudaMemsetAsync(fwd_first, 0xFF, bytes, s));
-    if (flags & FLAG_NODUPES)
-        CU(cudaMemsetAsync(fwd_last, 0xFF, bytes, s));
-    if (flags & FLAG_CONSISTENCY) {
-        CU(cudaMemsetAsync(rev_first, 0xFF, bytes, s));
+    if (search_needs_prefill(K, cols)) {
+        CU(cudaMemsetAsync(fwd_first, 0xFF, bytes, s));
         if (flags & FLAG_NODUPES)
-            CU(cudaMemsetAsync(rev_last, 0xFF, bytes, s));
+            CU(cudaMemsetAsync(fwd_last, 0xFF, bytes, s));
+        if (flags & FLAG_CONSISTENCY) {
+            CU(cudaMemsetAsync(rev_first, 0xFF, bytes, s));
+            if (flags & FLAG_NODUPES)
+                CU(cudaMemsetAsync(rev_last, 0xFF, bytes, s));
+        }
     }
-    CU(launch_search(desc0, desc1, K, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, s));
+    CU(launch_search(desc0, desc1, K, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, s, top_bit_free));
     h->launches += 1;
     return 0;
 }
@@ -766,6 +818,7 @@ int bicos_b200_match_host_begin(bicos_b200_handle h, const void* const* host_pla
         if (!host_planes0[i] || !host_planes1[i])
             return fail(BICOS_B200_ERR_INVALID, "image %d is null", i);
     DeviceGuard g(h->device);
+    Range nvtx_host("bicos_b200::match_host_begin");
 
     // Rows are independent, so the image is cut into row bands that flow through three
     // streams: band b+1 uploads while band b is matched and band b-1 downloads. With pinned
@@ -924,6 +977,8 @@ int bicos_b200_match_host_end(bicos_b200_handle h) {
     h->host_pending = false;
     CU(cudaStreamSynchronize(h->s_out));
     CU(cudaStreamSynchronize(h->s_compute));
+    if (int rc = check_search_timeout())
+        return rc;
     // pageable result buffers: out of the pinned images, a slice per host thread
     struct Piece {
         char* dst;
@@ -1020,6 +1075,8 @@ int bicos_b200_stage_times(bicos_b200_handle h, double* ms_out, long long* match
         return fail(BICOS_B200_ERR_INVALID, "null argument");
     DeviceGuard g(h->device);
     CU(cudaDeviceSynchronize());
+    if (int rc = check_search_timeout())
+        return rc;
     if (int rc = prof_collect(h))
         return rc;
     for (int st = 0; st < N_STAGES; ++st)
@@ -1034,7 +1091,7 @@ int bicos_b200_synchronize(bicos_b200_handle h, void* stream) {
         return fail(BICOS_B200_ERR_INVALID, "null handle");
     DeviceGuard g(h->device);
     CU(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
-    return 0;
+    return check_search_timeout();
 }
 
 long long bicos_b200_kernel_launches(bicos_b200_handle h) {
@@ -1050,6 +1107,10 @@ int bicos_b200_set_search_engine(int engine) {
 
 int bicos_b200_get_search_engine(void) {
     return search_engine();
+}
+
+const char* bicos_b200_last_search_kernel(void) {
+    return last_search_kernel();
 }
 
 } // extern "C"

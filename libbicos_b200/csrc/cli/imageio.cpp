@@ -50,6 +50,8 @@ GrayImage read_png(const std::vector<uint8_t>& file, const std::string& path, bo
             throw std::runtime_error(path + ": truncated PNG chunk");
         const uint8_t* body = &file[pos + 8];
         if (!std::memcmp(type, "IHDR", 4)) {
+            if (len != 13)
+                throw std::runtime_error(path + ": bad PNG IHDR length");
             width = be32(body);
             height = be32(body + 4);
             depth = body[8];
@@ -67,6 +69,9 @@ GrayImage read_png(const std::vector<uint8_t>& file, const std::string& path, bo
     }
     if (!have_ihdr || width == 0 || height == 0)
         throw std::runtime_error(path + ": PNG without IHDR");
+    // the library's own limits (include/bicos_b200.h: 32767 columns, 65535 rows): nothing larger is allocated
+    if (width > 32767u || height > 65535u)
+        throw std::runtime_error(path + ": PNG larger than 32767 x 65535");
     if (interlace != 0)
         throw std::runtime_error(path + ": interlaced PNG is not supported");
     int channels;
@@ -78,6 +83,8 @@ GrayImage read_png(const std::vector<uint8_t>& file, const std::string& path, bo
         case 6: channels = 4; break;
         default: throw std::runtime_error(path + ": bad PNG colour type");
     }
+    if (ctype == 3 && depth == 16)
+        throw std::runtime_error(path + ": palette PNG with 16-bit indices");
     if (!(depth == 8 || depth == 16 || (ctype == 0 && (depth == 1 || depth == 2 || depth == 4))
           || (ctype == 3 && (depth == 1 || depth == 2 || depth == 4))))
         throw std::runtime_error(path + ": unsupported PNG bit depth");

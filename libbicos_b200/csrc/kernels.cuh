@@ -74,8 +74,8 @@ cudaError_t launch_transform(
 
 // kernel 2: row-wise Hamming argmin, forward (per left pixel) and, with
 // FLAG_CONSISTENCY, the column-wise minima of the same W x W cost tile (reference a5/a6/a7).
-// All key arrays in use must be pre-filled with KEY_NONE by the caller (fwd_last / rev_last
-// are only touched with FLAG_NODUPES, rev_* only with FLAG_CONSISTENCY).
+// Key arrays in use must be pre-filled with KEY_NONE by the caller when search_needs_prefill()
+// says so (fwd_last / rev_last are only touched with FLAG_NODUPES, rev_* only with FLAG_CONSISTENCY).
 cudaError_t launch_search(
     const uint32_t* desc0,
     const uint32_t* desc1,
@@ -134,6 +134,14 @@ int search_mma_variant(); // tensor-core kernel variant, see search_mma.cu
 void set_search_mma_variant(int v);
 int search_engine(); // initial value: environment BICOS_B200_SEARCH_ENGINE = auto | popc | mma
 void set_search_engine(int engine);
+// Which kernel the calling thread's last launch_search dispatched, e.g. "mma2<K=4,nodupes=0,ct=1,dirs=2>" or
+// "popc<K=4,flags=2>" ("" before the first search): lets tests assert that the kernel they mean to cover ran.
+bool search_needs_prefill(int K, int cols); // must the caller fill the key arrays with KEY_NONE? (popcount engine only)
+const char* last_search_kernel();
+void note_search_kernel(const char* fmt, ...);
+// Nonzero once if a wait inside a tensor-core search kernel timed out (pipeline bug, or a device stalled for
+// longer than BICOS_B200_MMA_TIMEOUT_MS, default 10 s): its keys are garbage. Clears the flag.
+unsigned int search_mma_take_timeout();
 
 // kernel 3: postfilter (no-duplicates / left-right consistency) fused with the NXC
 // agree / agree_subpixel refinement (reference a7 tail, a8, a9, a10, a11)

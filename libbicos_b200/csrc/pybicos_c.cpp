@@ -126,9 +126,12 @@ BicosResult* BICOS_Match(void** stack0_data, int* stack0_rows, int* stack0_cols,
         cfg.nxcorr_threshold = config->nxcorr_threshold;
         cfg.subpixel_step = config->subpixel_step;
         cfg.min_variance = config->min_variance;
-        cfg.mode = config->mode;
-        cfg.precision = config->precision;
-        cfg.variant_type = config->variant_type;
+        // enums as the reference converts them (src/pybicos_c.cpp:56-89): any non-zero value is the second
+        // enumerator. In particular bit 1 of bicos_b200_config::mode (BICOS_B200_MODE_WIDE, an extension the
+        // reference does not have) cannot be reached through this ABI.
+        cfg.mode = config->mode != 0 ? 1 : 0;
+        cfg.precision = config->precision != 0 ? 1 : 0;
+        cfg.variant_type = config->variant_type != 0 ? 1 : 0;
         cfg.max_lr_diff = config->max_lr_diff;
         cfg.no_dupes = config->no_dupes;
 

@@ -35,6 +35,8 @@
 #include "kernels.cuh"
 
 #include <atomic>
+#include <stdarg.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -515,6 +517,7 @@ cudaError_t launch_search_popc(
 ) {
     if (rows <= 0 || cols <= 0 || cols > 32767)
         return cudaErrorInvalidValue;
+    note_search_kernel("popc<K=%d,flags=%d>", K, flags);
     switch (K) {
         case 1:
             return launch_k<1>(desc0, desc1, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, stream);
@@ -534,6 +537,18 @@ cudaError_t launch_search_popc(
 
 namespace {
 std::atomic<int> g_engine { -1 };
+thread_local char g_last_kernel[96] = "";
+}
+
+const char* last_search_kernel() {
+    return g_last_kernel;
+}
+
+void note_search_kernel(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_kernel, sizeof g_last_kernel, fmt, ap);
+    va_end(ap);
 }
 
 int search_engine() {
@@ -548,6 +563,11 @@ int search_engine() {
 
 void set_search_engine(int engine) {
     g_engine.store(engine < 0 || engine > 2 ? 0 : engine, std::memory_order_relaxed);
+}
+
+bool search_needs_prefill(int K, int cols) {
+    const int engine = search_engine();
+    return !(engine == 2 || (engine == 0 && search_mma_supports(K, cols)));
 }
 
 cudaError_t launch_search(

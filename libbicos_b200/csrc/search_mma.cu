@@ -44,9 +44,12 @@
 
 #include "kernels.cuh"
 
+#include <atomic>
 #include <limits.h>
+#include <mutex>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace bicos_b200 {
 namespace {
@@ -89,17 +92,55 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 
-// A wait that cannot hang the device: a pipeline bug traps (the launch then fails with an
-// error the C ABI reports) instead of spinning forever.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins)
-        if (spins > (1u << 20)) {
+// A wait that cannot hang the device and does not kill the context either. Fast path: one try_wait. Slow
+// path (out of line): try_wait with __nanosleep back-off under a wall-clock bound read from %globaltimer
+// (seconds, MmaArgs::timeout_ns; a bound in iterations would depend on how long try_wait suspends and could
+// expire under a debugger, compute-sanitizer or time-slicing). When the bound expires the thread raises the
+// CTA's abort word in shared memory and a flag in mapped host memory, every other role sees the abort word
+// in its own slow path, all roles leave their loops and the kernel ends normally: the key arrays are then
+// garbage, and the C ABI reports "search pipeline timeout" at its next synchronisation point
+// (search_mma_take_timeout) instead of the process losing its CUDA context to a trap.
+struct Watch {
+    unsigned int* flag; // mapped host memory, see mma_timeout_flag()
+    unsigned long long timeout_ns;
+    unsigned int abort;
+};
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, Watch* watch) {
+    const unsigned long long t0 = global_ns();
+    unsigned int pause = 32;
+    for (;;) {
+#pragma unroll 1
+        for (int i = 0; i < 32; ++i)
+            if (mbar_try(bar, parity))
+                return true;
+        if (*(volatile unsigned int*)&watch->abort)
+            return false;
+        if (global_ns() - t0 > watch->timeout_ns) {
 #ifdef BICOS_MMA_DEBUG
             printf("mbar timeout: block %d warp %d lane %d barrier +%u parity %u\n", blockIdx.x, threadIdx.x >> 5, threadIdx.x & 31,
                    bar & 1023u, parity);
 #endif
-            __trap();
+            *(volatile unsigned int*)&watch->abort = 1u;
+            if (watch->flag)
+                *(volatile unsigned int*)watch->flag = 1u + blockIdx.x;
+            return false;
         }
+        __nanosleep(pause);
+        pause = pause < 1024 ? pause * 2 : 1024;
+    }
+}
+
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, Watch* watch) {
+    if (mbar_try(bar, parity))
+        return true;
+    return mbar_wait_slow(bar, parity, watch);
 }
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -414,6 +455,8 @@ struct MmaArgs {
     uint32_t* fwd_last;
     uint32_t* rev_first; // direction 1: per right pixel over the left row
     uint32_t* rev_last;
+    unsigned int* timeout_flag; // mapped host word a timed-out wait raises (mbar_wait_slow)
+    unsigned long long timeout_ns;
 };
 
 // right-tile stages and left-tile buffers in shared memory: what fits beside a second CTA (K <= 8) or alone
@@ -459,6 +502,7 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
     // packed full [NP], packed free [NP]
     __shared__ uint64_t bars[2 * NS + 4 + NA + 2 * NP];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ Watch s_watch;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -479,6 +523,9 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
     const uint32_t s_packed = s_b + NS * KA * ATOM_BYTES; // + packed stage * PACKED_BYTES
 
     if (tid == 0) {
+        s_watch.flag = p.timeout_flag;
+        s_watch.timeout_ns = p.timeout_ns;
+        s_watch.abort = 0;
         for (int s = 0; s < NS; ++s) {
             mbar_init(bar_stage_full + 8 * s, TN);
             mbar_init(bar_stage_free + 8 * s, 1);
@@ -521,12 +568,15 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
             uint32_t b = 0, left_phase = 0;
             int g = 0;
             for (int n = 0; n < nitems; ++n) {
-                mbar_wait(bar_left_full + 8 * b, left_phase);
+                if (!mbar_wait(bar_left_full + 8 * b, left_phase, &s_watch))
+                    goto teardown;
                 const uint64_t desc_a = desc_a0 + b * STAGE_STEP;
                 for (int t = 0; t < ntiles; ++t, ++g) {
-                    mbar_wait(bar_stage_full + 8 * s, stage_phase);
+                    if (!mbar_wait(bar_stage_full + 8 * s, stage_phase, &s_watch))
+                        goto teardown;
                     if (g >= 2)
-                        mbar_wait(bar_acc_drained + 8 * a, ((g - 2) >> 1) & 1); // the epilogue has read this accumulator
+                        if (!mbar_wait(bar_acc_drained + 8 * a, ((g - 2) >> 1) & 1, &s_watch)) // the epilogue has read this accumulator
+                            goto teardown;
                     tc_fence_after();
                     const uint64_t desc_b = desc_b0 + s * STAGE_STEP;
                     if (elect_one()) {
@@ -567,7 +617,8 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
                 for (int t = 0; t < ntiles; ++t, ++f) {
                     const int s = f % NP;
                     if (f >= NP)
-                        mbar_wait(bar_packed_free + 8 * s, (f / NP - 1) & 1);
+                        if (!mbar_wait(bar_packed_free + 8 * s, (f / NP - 1) & 1, &s_watch))
+                            goto teardown;
                     const uint32_t bytes = (uint32_t)min(TN, cols - t * TN) * K * 4;
                     mbar_expect_tx(bar_packed_full + 8 * s, bytes);
                     bulk_copy_g2s(s_packed + (uint32_t)(s * PACKED_BYTES), row + (size_t)t * TN * K, bytes, bar_packed_full + 8 * s);
@@ -585,14 +636,16 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
         for (int g = 0; g < total; ++g) {
             const int ps = g % NP, s = g % NS;
             const int valid = min(TN, cols - t * TN); // the last tile of a row may be short: repeat its last pixel
-            mbar_wait(bar_packed_full + 8 * ps, (g / NP) & 1);
+            if (!mbar_wait(bar_packed_full + 8 * ps, (g / NP) & 1, &s_watch))
+                goto teardown;
             uint4 d[KA];
             const uint32_t src = s_packed + (uint32_t)(ps * PACKED_BYTES) + (uint32_t)min(r, valid - 1) * (K * 4);
 #pragma unroll
             for (int q = 0; q < KA; ++q)
                 d[q] = ld_shared_v4(src + 16 * q);
             if (g >= NS)
-                mbar_wait(bar_stage_free + 8 * s, (g / NS - 1) & 1); // the MMAs that read this stage are done
+                if (!mbar_wait(bar_stage_free + 8 * s, (g / NS - 1) & 1, &s_watch)) // the MMAs that read this stage are done
+                    goto teardown;
             expand_pixel<K, true, CT>(d, s_b + (uint32_t)(s * KA * ATOM_BYTES), r);
             // only now: the stores above consumed the loaded registers, so the packed slot has been read
             // (an arrive right after the loads was observed to let the next bulk copy overtake them)
@@ -637,7 +690,8 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
                 load_left(nx, dl); // in flight over the first tiles of this item
             for (int t = 0; t < ntiles; ++t, ++g) {
                 const int a = g & 1;
-                mbar_wait(bar_acc_full + 8 * a, (g >> 1) & 1);
+                if (!mbar_wait(bar_acc_full + 8 * a, (g >> 1) & 1, &s_watch))
+                    goto teardown;
                 tc_fence_after();
                 const uint32_t acc = lane_base + (uint32_t)(a * TN);
                 const int tile0 = t * TN;
@@ -705,6 +759,7 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 8) ? 2 : 1) search_mma_kernel(
         }
     }
 
+teardown:
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -768,6 +823,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
     // see only every second phase, and a parity wait two phases ahead of the barrier succeeds at once.
     __shared__ uint64_t bars[2 * NS + 2 * NP + 12 + NA];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ Watch s_watch;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -788,6 +844,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
     const uint32_t bar_left_full = bar_acc_drained + 48;
 
     if (tid == 0) {
+        s_watch.flag = p.timeout_flag;
+        s_watch.timeout_ns = p.timeout_ns;
+        s_watch.abort = 0;
         for (int s = 0; s < NS; ++s) {
             mbar_init(bar_stage_full + 8 * s, TN);
             mbar_init(bar_stage_free + 8 * s, 2);
@@ -829,13 +888,16 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
             uint32_t b = 0, left_phase = 0;
             int q = h; // MMA group 2 g + h
             for (int n = 0; n < nitems; ++n) {
-                mbar_wait(bar_left_full + 8 * b, left_phase);
+                if (!mbar_wait(bar_left_full + 8 * b, left_phase, &s_watch))
+                    goto teardown;
                 const uint32_t left = u_tmem + V2_ACC_COLS + b * LEFT_COLS + (uint32_t)(h * 32 * KA);
                 for (int t = 0; t < ntiles; ++t, q += 2) {
                     const uint32_t a = (uint32_t)q % 3u;
-                    mbar_wait(bar_stage_full + 8 * s, stage_phase);
+                    if (!mbar_wait(bar_stage_full + 8 * s, stage_phase, &s_watch))
+                        goto teardown;
                     if (q >= 3) // the accumulator's previous use, by the other half, has been read
-                        mbar_wait(bar_acc_drained + 8 * (2 * a + (1 - h)), (((uint32_t)q - 3u) / 6u) & 1u);
+                        if (!mbar_wait(bar_acc_drained + 8 * (2 * a + (1 - h)), (((uint32_t)q - 3u) / 6u) & 1u, &s_watch))
+                            goto teardown;
                     tc_fence_after();
                     const uint64_t desc_b = desc_b0 + s * STAGE_STEP;
                     if (elect_one()) {
@@ -874,7 +936,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
                 for (int t = 0; t < ntiles; ++t, ++f) {
                     const int s = f % NP;
                     if (f >= NP)
-                        mbar_wait(bar_packed_free + 8 * s, (f / NP - 1) & 1);
+                        if (!mbar_wait(bar_packed_free + 8 * s, (f / NP - 1) & 1, &s_watch))
+                            goto teardown;
                     const uint32_t bytes = (uint32_t)min(TN, cols - t * TN) * K * 4;
                     mbar_expect_tx(bar_packed_full + 8 * s, bytes);
                     bulk_copy_g2s(s_packed + (uint32_t)(s * PACKED_BYTES), row + (size_t)t * TN * K, bytes, bar_packed_full + 8 * s);
@@ -890,14 +953,16 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
         for (int g = 0; g < total; ++g) {
             const int ps = g % NP, s = g % NS;
             const int valid = min(TN, cols - t * TN);
-            mbar_wait(bar_packed_full + 8 * ps, (g / NP) & 1);
+            if (!mbar_wait(bar_packed_full + 8 * ps, (g / NP) & 1, &s_watch))
+                goto teardown;
             uint4 d[KA];
             const uint32_t src = s_packed + (uint32_t)(ps * PACKED_BYTES) + (uint32_t)min(r, valid - 1) * (K * 4);
 #pragma unroll
             for (int q = 0; q < KA; ++q)
                 d[q] = ld_shared_v4(src + 16 * q);
             if (g >= NS)
-                mbar_wait(bar_stage_free + 8 * s, (g / NS - 1) & 1);
+                if (!mbar_wait(bar_stage_free + 8 * s, (g / NS - 1) & 1, &s_watch))
+                    goto teardown;
             expand_pixel<K, true, CT>(d, s_b + (uint32_t)(s * KA * ATOM_BYTES), r);
             mbar_arrive(bar_packed_free + 8 * ps); // after the stores that consumed the loaded registers
             fence_async_smem();
@@ -941,7 +1006,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
                 load_left(nx, dl);
             for (int t = 0; t < ntiles; ++t, ++g) {
                 const int q = 2 * g + h, a = q % 3;
-                mbar_wait(bar_acc_full + 8 * (2 * a + h), ((uint32_t)q / 6u) & 1u);
+                if (!mbar_wait(bar_acc_full + 8 * (2 * a + h), ((uint32_t)q / 6u) & 1u, &s_watch))
+                    goto teardown;
                 tc_fence_after();
                 const uint32_t acc = lane_base + (uint32_t)(a * TN);
                 const int tile0 = t * TN;
@@ -1004,6 +1070,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
         }
     }
 
+teardown:
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -1105,7 +1172,57 @@ int search_mma_smem_bytes(int K) {
 }
 
 namespace {
-int g_variant = -1;
+std::atomic<int> g_variant { -1 };
+std::atomic<int> g_colterm { -1 };
+std::atomic<long long> g_timeout_ms { -1 };
+std::atomic<unsigned int*> g_timeout_flag { nullptr };
+std::mutex g_timeout_mutex;
+
+// One word of mapped, portable host memory that a timed-out wait of either kernel raises (mbar_wait_slow):
+// the host can read it at any time without touching the device. Null if the allocation fails (the kernels
+// then only abort, and the corrupt keys go unreported -- better than refusing to search).
+unsigned int* mma_timeout_flag() {
+    unsigned int* f = g_timeout_flag.load(std::memory_order_acquire);
+    if (f)
+        return f;
+    std::lock_guard<std::mutex> lk(g_timeout_mutex);
+    f = g_timeout_flag.load(std::memory_order_acquire);
+    if (!f) {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, 64, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        memset(p, 0, 64);
+        f = static_cast<unsigned int*>(p);
+        g_timeout_flag.store(f, std::memory_order_release);
+    }
+    return f;
+}
+
+unsigned long long mma_timeout_ns() {
+    long long ms = g_timeout_ms.load(std::memory_order_relaxed);
+    if (ms < 0) {
+        const char* v = getenv("BICOS_B200_MMA_TIMEOUT_MS");
+        ms = v ? atoll(v) : 0;
+        if (ms <= 0)
+            ms = 10000; // a whole search of the largest configuration takes < 0.1 s
+        g_timeout_ms.store(ms, std::memory_order_relaxed);
+    }
+    return (unsigned long long)ms * 1000000ull;
+}
+} // namespace
+
+// Nonzero (1 + the CTA that gave up) if a wait of a tensor-core search kernel timed out since the last call;
+// clears the flag. The C ABI asks at its synchronisation points and turns it into an error.
+unsigned int search_mma_take_timeout() {
+    unsigned int* f = g_timeout_flag.load(std::memory_order_acquire);
+    if (!f)
+        return 0;
+    const unsigned int v = *(volatile unsigned int*)f;
+    if (v)
+        *(volatile unsigned int*)f = 0;
+    return v;
 }
 
 // 1 = two CTAs per SM, both operands in shared memory; 2 = one CTA per SM, left operand in tensor memory
@@ -1114,33 +1231,33 @@ int g_variant = -1;
 // columns; small images are served better by the finer items of variant 1). Environment
 // BICOS_B200_MMA_VARIANT = 1 | 2 overrides for A/B timing.
 int search_mma_variant() {
-    if (g_variant < 0) {
+    int g = g_variant.load(std::memory_order_relaxed);
+    if (g < 0) {
         const char* v = getenv("BICOS_B200_MMA_VARIANT");
-        g_variant = v && v[0] == '2' ? 2 : v && v[0] == '1' ? 1 : 0;
+        g = v && v[0] == '2' ? 2 : v && v[0] == '1' ? 1 : 0;
+        g_variant.store(g, std::memory_order_relaxed);
     }
-    return g_variant;
+    return g;
 }
 
 void set_search_mma_variant(int v) {
-    g_variant = v == 2 ? 2 : v == 1 ? 1 : 0;
-}
-
-namespace {
-int g_colterm = -1;
+    g_variant.store(v == 2 ? 2 : v == 1 ? 1 : 0, std::memory_order_relaxed);
 }
 
 // Whether descriptors with a free top bit take the column-term kernels (fold32): environment
 // BICOS_B200_MMA_COLTERM = 0 | 1, default BICOS_MMA_COLTERM_DEFAULT.
 bool search_mma_colterm() {
-    if (g_colterm < 0) {
+    int g = g_colterm.load(std::memory_order_relaxed);
+    if (g < 0) {
         const char* v = getenv("BICOS_B200_MMA_COLTERM");
-        g_colterm = v ? (v[0] == '1') : BICOS_MMA_COLTERM_DEFAULT;
+        g = v ? (v[0] == '1') : BICOS_MMA_COLTERM_DEFAULT;
+        g_colterm.store(g, std::memory_order_relaxed);
     }
-    return g_colterm == 1;
+    return g == 1;
 }
 
 void set_search_mma_colterm(bool on) {
-    g_colterm = on ? 1 : 0;
+    g_colterm.store(on ? 1 : 0, std::memory_order_relaxed);
 }
 
 bool search_mma_supports(int K, int cols) {
@@ -1178,6 +1295,8 @@ cudaError_t launch_search_mma(
     p.fwd_last = fwd_last;
     p.rev_first = rev_first;
     p.rev_last = rev_last;
+    p.timeout_flag = mma_timeout_flag();
+    p.timeout_ns = mma_timeout_ns();
     const int dirs = (flags & FLAG_CONSISTENCY) ? 2 : 1;
     const bool nodupes = (flags & FLAG_NODUPES) != 0;
     const long long pair_items = (long long)dirs * rows * ((cols + 2 * TM - 1) / (2 * TM));
@@ -1185,6 +1304,7 @@ cudaError_t launch_search_mma(
     const bool v2 = (K == 4 || K == 8) && (variant == 2 || (variant == 0 && pair_items >= 2 * sm_count_of_current_device()));
     // column term through the MMA (see fold32): only where the caller vouches for the free top bit
     const bool ct = top_bit_free && (K == 4 || K == 8) && search_mma_colterm();
+    note_search_kernel("mma%d<K=%d,nodupes=%d,ct=%d,dirs=%d>", v2 ? 2 : 1, K, (int)nodupes, (int)ct, dirs);
 #define BICOS_MMA_DISPATCH(LAUNCH, KK)                                                                      \
     (ct ? (nodupes ? LAUNCH<KK, true, true>(p, dirs, stream) : LAUNCH<KK, false, true>(p, dirs, stream))      \
         : (nodupes ? LAUNCH<KK, true, false>(p, dirs, stream) : LAUNCH<KK, false, false>(p, dirs, stream)))

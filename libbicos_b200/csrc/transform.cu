@@ -16,7 +16,7 @@
 //
 // The mean comparison `(float)p < fl(sum/n)` is evaluated as `p*n < sum` in integers:
 // identical for n <= 65 and 16-bit pixels (gap 1/n exceeds half an ulp of any float
-// below 65536; see DESIGN.md, checked by tests/test_transform.py against the oracle).
+// below 65536; see DESIGN.md, checked by tests/test_oracle.py::test_integer_mean_comparison_is_exact and tests/test_gpu_parity.py::test_transform_bit_exact).
 
 #include "kernels.cuh"
 

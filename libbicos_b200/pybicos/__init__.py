@@ -9,7 +9,7 @@ variant, ``set_no_duplicates()``, ``set_consistency(max_lr_diff, no_dupes)``), t
 It binds the six symbols of include/pybicos_c.h exported by the ``pybicos_c.so`` next to this
 file. That library is ABI-compatible with the reference's, so the reference's own, unmodified
 ``pybicos/__init__.py`` also works when this ``pybicos_c.so`` is dropped beside it (see
-INTEGRATION.md; tests/test_pybicos.py exercises both). One deliberate difference: with the
+INTEGRATION.md; tests/test_abi.py and tests/test_gpu_parity.py::test_pybicos_drop_in exercise both). One deliberate difference: with the
 threshold unset, ``match`` returns ``corrmap=None`` instead of raising on the empty corrmap.
 """
 

@@ -132,3 +132,37 @@ def test_reference_pybicos_module_loads_our_library(built, tmp_path):
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     assert out.stdout.strip() == "0.5 {'type': 'Consistency', 'max_lr_diff': 2, 'no_dupes': True} DOUBLE"
+
+
+def test_reference_signature_with_opencv_types():
+    """-DBICOS_WITH_OPENCV: BICOS::match takes cv::cuda::GpuMat images and a cv::cuda::Stream& as the reference does
+    (include/match.hpp:31-41). Compile-only, against the stand-in headers of oracle/shim."""
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-DBICOS_WITH_OPENCV", "-I" + os.path.join(ROOT, "oracle", "shim"),
+           "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
+           os.path.join(ROOT, "tests", "cpp", "opencv_signature_check.cpp")]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+
+
+def test_host_out_buffers_are_validated_before_any_device_work(built):
+    """Handle.match_host(out=...) refuses buffers of the wrong dtype / shape / layout before the C ABI is called
+    (so this runs without a GPU: the check needs only the pure type queries of the library)."""
+    import libbicos_b200 as lb
+
+    h = lb.Handle.__new__(lb.Handle)  # no device needed for the validation path
+    h._h = None
+    left = np.zeros((3, 8, 16), np.uint8)
+    cfg = lb.Config(nxcorr_threshold=0.5)
+    good = np.empty((8, 16), np.float32)
+    for out in ((np.empty((8, 16), np.int16), good), (good, None), (good, np.empty((8, 16), np.float64)),
+                (np.empty((16, 8), np.float32).T, good), (np.empty((4, 16), np.float32), good), good):
+        with pytest.raises(lb.BicosError, match="out "):
+            h.match_host_begin(left, left, cfg, out=out)
+    with pytest.raises(lb.BicosError, match="out corrmap must be None"):
+        h.match_host_begin(left, left, lb.Config(nxcorr_threshold=None), out=(np.empty((8, 16), np.int16), good))
+
+
+def test_last_search_kernel_starts_empty(built):
+    import libbicos_b200 as lb
+
+    assert isinstance(lb.last_search_kernel(), str)

@@ -179,6 +179,50 @@ def test_match_float_parity(handle, oracles, n, dtype, rows, cols, kw):
     assert both.mean() > 0.2 or n <= 5, "test scene should have valid matches"
 
 
+# The kernels behind the headline numbers: variant 2 of the tensor-core search (one CTA per SM, left operand in
+# TMEM) is only dispatched when the image has at least two (direction, row, 256-pixel) items per SM, and the
+# column-term form only through bicos_b200_match. These scenes are large enough for both and small enough for the
+# oracle; bicos_b200_last_search_kernel() proves which kernel ran, so a change of the dispatch rule cannot
+# silently take them out of the suite.
+BENCHED = [
+    # n, dtype, rows, cols, config, kernel expected on a 148-SM B200
+    (33, np.uint8, 160, 512, dict(nxcorr_threshold=0.96, min_variance=2.0, subpixel_step=0.1, consistency=True, max_lr_diff=1),
+     "mma2<K=4,nodupes=0,ct=1,dirs=2>"),  # the bench workload's configuration
+    (33, np.uint8, 152, 520, dict(nxcorr_threshold=0.96, min_variance=2.0), "mma2<K=4,nodupes=1,ct=1,dirs=1>"),  # C1, ragged last tile
+    (33, np.uint8, 160, 512, dict(nxcorr_threshold=0.9, subpixel_step=0.25, consistency=True, max_lr_diff=2, no_dupes=True),
+     "mma2<K=4,nodupes=1,ct=1,dirs=2>"),
+    (64, np.uint8, 160, 512, dict(nxcorr_threshold=0.9, min_variance=2.0), "mma2<K=8,nodupes=1,ct=1,dirs=1>"),  # C4: 256 bits
+    (64, np.uint8, 100, 700, dict(nxcorr_threshold=0.9, subpixel_step=0.2, consistency=True, max_lr_diff=1),
+     "mma2<K=8,nodupes=0,ct=1,dirs=2>"),
+    (16, np.uint16, 160, 512, dict(nxcorr_threshold=0.9, mode_full=True, consistency=True, max_lr_diff=1, no_dupes=True),
+     "mma2<K=8,nodupes=1,ct=1,dirs=2>"),  # C3: FULL, u16
+]
+
+
+@pytest.mark.parametrize("n,dtype,rows,cols,kw,kernel", BENCHED)
+@pytest.mark.parametrize("double", [False, True])
+def test_match_parity_on_the_benchmarked_kernels(handle, oracles, n, dtype, rows, cols, kw, kernel, double):
+    import torch
+
+    if torch.cuda.get_device_properties(0).multi_processor_count != 148:
+        pytest.skip("kernel expectations are for the 148 SMs of a B200")
+    left, right, _ = synth.make_stacks(n, 1024, cols, dtype, seed=7 * n + rows, row0=300, rows=rows)
+    want_d, want_c = oracles.port.match(left, right, double=double, **kw)
+    lb.set_search_engine("auto")
+    disp, corr = handle.match(_cuda(left), _cuda(right), Config(double=double, **kw))
+    assert lb.last_search_kernel() == kernel
+    got_d, got_c = disp.cpu().numpy(), corr.cpu().numpy()
+    invalid_w = np.isnan(want_d) | (want_d == -32768)
+    invalid_g = np.isnan(got_d) | (got_d == -32768)
+    assert np.array_equal(invalid_g, invalid_w), "valid masks differ"
+    assert np.array_equal(np.isnan(got_c), np.isnan(want_c))
+    ok = ~np.isnan(want_c)
+    assert np.max(np.abs(got_c[ok] - want_c[ok]), initial=0) <= (1e-12 if double else 1e-5)
+    assert np.max(np.abs(got_d[~invalid_w] - want_d[~invalid_w]), initial=0) <= 1e-3
+    assert _same(got_d, want_d) and _same(got_c, want_c)  # in fact identical
+    assert (~invalid_w).mean() > 0.3, "test scene should have valid matches"
+
+
 @pytest.mark.parametrize("n,dtype,rows,cols,kw", [c for c in CASES if c[4].get("nxcorr_threshold") is not None][:8])
 def test_match_double_parity(handle, oracles, n, dtype, rows, cols, kw):
     left, right, _ = synth.make_stacks(n, 512, cols, dtype, seed=3 * n + cols, row0=64, rows=rows)
@@ -279,11 +323,16 @@ def test_search_wide_rows_split_units(handle, oracles, engine, k, cols, flags):
 
 
 @pytest.mark.parametrize("k,rows,cols,flags", [(4, 700, 384, 3), (4, 40, 2048, 2), (8, 500, 300, 1), (8, 12, 2448, 3),
-                                               (12, 330, 256, 2), (16, 310, 200, 3), (4, 1300, 130, 0)])
-def test_search_engines_identical(handle, k, rows, cols, flags):
+                                               (12, 330, 256, 2), (16, 310, 200, 3), (4, 1300, 130, 0), (4, 90, 1000, 2),
+                                               (8, 200, 520, 2)])
+@pytest.mark.parametrize("top_bit_free", [False, True])
+def test_search_engines_identical(handle, oracles, k, rows, cols, flags, top_bit_free):
     """The tensor-core engine (int8 GEMM + argmin epilogue) reproduces the popcount engine's four key arrays bit
     for bit, at sizes where a persistent CTA walks several work items (rows x M tiles x directions > resident CTAs)
-    and with descriptors drawn from a small pool, so that exact ties are the rule."""
+    and with descriptors drawn from a small pool, so that exact ties are the rule. With `top_bit_free` the top
+    descriptor bit is clear and the tensor-core engine is told so (BICOS_B200_FLAG_TOP_BIT_FREE): the column-term
+    kernels bicos_b200_match uses, in both kernel variants. The postfiltered disparity of the tensor-core keys is
+    also compared with the oracle's bicos()."""
     import torch
 
     rng = np.random.default_rng(k + rows + cols + flags)
@@ -292,10 +341,13 @@ def test_search_engines_identical(handle, k, rows, cols, flags):
     def draw():
         d = pool[rng.integers(0, len(pool), size=(rows, cols))]
         flip = rng.integers(0, 4, size=(rows, cols, 1)) > 1
-        bit = rng.integers(0, 32 * k, size=(rows, cols))
+        bit = rng.integers(0, 32 * k - 1, size=(rows, cols))
         mask = np.zeros((rows, cols, k), dtype=np.uint32)
         np.put_along_axis(mask, (bit // 32)[..., None], (np.uint32(1) << (bit % 32).astype(np.uint32))[..., None], axis=2)
-        return d ^ (mask * flip)
+        d = d ^ (mask * flip)
+        if top_bit_free:
+            d[..., k - 1] &= np.uint32(0x7FFFFFFF)
+        return d
 
     pitch = (cols * k + 3) // 4 * 4
 
@@ -304,18 +356,33 @@ def test_search_engines_identical(handle, k, rows, cols, flags):
         buf[:, : cols * k] = d.reshape(rows, cols * k)
         return torch.from_numpy(buf.view(np.int32)).cuda()
 
-    d0, d1 = pitched(draw()), pitched(draw())
-    got = {}
+    n0, n1 = draw(), draw()
+    d0, d1 = pitched(n0), pitched(n1)
+    got, keys = {}, None
     try:
         for name in ("popc", "tensor"):
             lb.set_search_engine(name)
-            got[name] = [None if a is None else a.cpu().numpy() for a in handle.search(d0, d1, k, cols, flags)]
+            keys = handle.search(d0, d1, k, cols, flags, top_bit_free=top_bit_free)
+            got[name] = [None if a is None else a.cpu().numpy() for a in keys]
+            kernel = lb.last_search_kernel()
+            assert kernel.startswith("popc<" if name == "popc" else "mma"), kernel
     finally:
         lb.set_search_engine("auto")
+    assert f"ct={int(top_bit_free and k in (4, 8))}" in kernel, kernel
+    if torch.cuda.get_device_properties(0).multi_processor_count == 148:
+        dirs = 2 if flags & FLAG_CONSISTENCY else 1
+        v2 = k in (4, 8) and dirs * rows * ((cols + 255) // 256) >= 296
+        assert kernel.startswith("mma2<" if v2 else "mma1<"), kernel
     for a, b, what in zip(got["popc"], got["tensor"], ("fwd_first", "fwd_last", "rev_first", "rev_last")):
         assert (a is None) == (b is None)
         if a is not None:
             assert np.array_equal(a, b), f"{what}: {(a != b).sum()} of {a.size} keys differ"
+    if flags:  # flags 0 (plain first minimum) is a building block no Config reaches
+        want = oracles.port.bicos(n0, n1, flags, 2)
+        dummy = torch.zeros((2, rows, cols), dtype=torch.uint8, device="cuda")
+        cfg = Config(nxcorr_threshold=None, consistency=bool(flags & FLAG_CONSISTENCY), max_lr_diff=2, no_dupes=flags == 3)
+        disp, _, _ = handle.refine(dummy, dummy, cfg, keys)
+        assert np.array_equal(disp.cpu().numpy(), want)
 
 
 def test_tensor_engine_refuses_what_it_cannot_do(handle):
@@ -468,6 +535,58 @@ def test_match_host_pipelined(handle, oracles):
     for (d, c), (wd, wc) in zip(got, want):
         assert _same(d, wd) and _same(c, wc)
     other.close()
+
+
+def test_out_buffers_are_validated(handle):
+    """Caller-supplied output buffers of the wrong type, shape, device or layout are refused before any kernel
+    or copy can write past them (the C ABI takes plain pointers and trusts them)."""
+    import torch
+
+    left, right, _ = synth.make_stacks(9, 32, 64, np.uint8, seed=3)
+    l, r = _cuda(left), _cuda(right)
+    thr, nothr = Config(nxcorr_threshold=0.5), Config(nxcorr_threshold=None)
+    f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device="cuda")  # noqa: E731
+    i16 = torch.empty((32, 64), dtype=torch.int16, device="cuda")
+    handle.match(l, r, thr, out=(f32(32, 64), f32(32, 64)))
+    handle.match(l, r, nothr, out=(i16, None))
+    for cfg, out in ((thr, (i16, f32(32, 64))),  # int16 disparity buffer with a thresholded (float32) configuration
+                     (thr, (f32(32, 64), None)),  # threshold set but no corrmap buffer
+                     (thr, (f32(32, 64), torch.empty((32, 64), dtype=torch.float64, device="cuda"))),  # float64 corrmap, SINGLE
+                     (Config(nxcorr_threshold=0.5, double=True), (f32(32, 64), f32(32, 64))),  # float32 corrmap, DOUBLE
+                     (thr, (f32(16, 64), f32(32, 64))),  # too small
+                     (thr, (f32(64, 32).t(), f32(32, 64))),  # transposed view
+                     (thr, (torch.empty((32, 64), dtype=torch.float32), f32(32, 64))),  # host tensor
+                     (nothr, (i16, f32(32, 64)))):  # corrmap without a threshold
+        with pytest.raises(lb.BicosError, match="out "):
+            handle.match(l, r, cfg, out=out)
+    good = (np.empty((32, 64), np.float32), np.empty((32, 64), np.float32))
+    handle.match_host(left, right, thr, out=good)
+    for out in ((np.empty((32, 64), np.int16), good[1]), (good[0], None), (np.empty((64, 32), np.float32).T, good[1]),
+                (np.empty((32, 32), np.float32), good[1])):
+        with pytest.raises(lb.BicosError, match="out "):
+            handle.match_host(left, right, thr, out=out)
+
+
+def test_matches_on_different_streams_share_the_workspace_safely(handle, oracles):
+    """Two matches enqueued back to back on different streams through one handle: the second waits on the device
+    for the first (it reuses the descriptor and key buffers), so both results are right."""
+    import torch
+
+    kw = dict(nxcorr_threshold=0.9, subpixel_step=0.2, consistency=True, max_lr_diff=1)
+    a = synth.make_stacks(33, 160, 512, np.uint8, seed=21)[:2]
+    b = synth.make_stacks(33, 160, 512, np.uint8, seed=22)[:2]
+    want = [oracles.port.match(l, r, **kw) for l, r in (a, b)]
+    dev = [(_cuda(l), _cuda(r)) for l, r in (a, b)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for rep in range(3):
+        got = []
+        for (l, r), st in zip(dev, streams):
+            with torch.cuda.stream(st):
+                got.append(handle.match(l, r, Config(**kw)))
+        torch.cuda.synchronize()
+        for (d, c), (wd, wc) in zip(got, want):
+            assert _same(d.cpu().numpy(), wd) and _same(c.cpu().numpy(), wc), rep
 
 
 def test_errors(handle):
