@@ -112,7 +112,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
-__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, Watch* watch) {
+__device__ __forceinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, Watch* watch) {
     const unsigned long long t0 = global_ns();
     unsigned int pause = 32;
     for (;;) {
@@ -776,8 +776,35 @@ teardown:
 // 128 x 128 of output). TMEM: three 128-column accumulators in rotation (columns 0..383) + the left
 // operand, 2 x 32 columns per 128 descriptor bits, double-buffered for 128 bits (columns 384..511).
 //   warps 0-3 / 4-7  epilogue of the first / second 128 left pixels (the four lane quadrants each)
-//   warps 8-11       producers        warps 12, 13  MMA issuers (one per half)        warp 14  loader
-constexpr int V2_THREADS = 480;
+//   warps 8-11       producers        warps 12, 13  MMA issuers (one per half)        warp 14  loader   warp 15  idle
+// Registers: only the epilogue needs many (the 64 accumulator registers of a tile). The kernel is compiled for
+// V2_REGS_LAUNCH registers per thread and the roles re-balance them with setmaxnreg, which works on warpgroups of
+// four warps (hence the idle sixteenth warp): the two epilogue warpgroups grow to V2_REGS_EPILOGUE, the producer
+// warpgroup shrinks to V2_REGS_PRODUCER, the issuer / loader warpgroup to V2_REGS_ISSUER. The CTA then holds
+// 512 x 80 = 40 960 of the SM's 65 536 registers instead of 480 x 128 = 61 440, so that a CTA of another kernel
+// (the FP32-bound refine of the previous band or frame, 128 threads x 168 registers, 34 KB of shared memory) fits
+// beside it and uses the issue slots and the FMA pipe this tensor-pipe-bound kernel leaves idle (cabi.cu, pipeline).
+constexpr int V2_THREADS = 512;
+template<int K>
+constexpr int V2_REGS_LAUNCH = K == 4 ? 80 : 96; // 256-bit descriptors: 32-bit folds, twice the left operand
+template<int K>
+constexpr int V2_REGS_EPILOGUE = K == 4 ? 120 : 136; // 256 threads
+template<int K>
+constexpr int V2_REGS_PRODUCER = K == 4 ? 40 : 48; // 128 threads
+template<int K>
+constexpr int V2_REGS_ISSUER = 40; // 128 threads (K only keeps the three budgets uniform to use)
+template<int K>
+constexpr bool V2_REGS_FIT = 256 * V2_REGS_EPILOGUE<K> + 128 * V2_REGS_PRODUCER<K> + 128 * V2_REGS_ISSUER<K> <= V2_THREADS * V2_REGS_LAUNCH<K>;
+static_assert(V2_REGS_FIT<4> && V2_REGS_FIT<8>, "the warpgroups cannot take more registers than the CTA was launched with");
+
+template<int REGS>
+__device__ __forceinline__ void regs_grow() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS));
+}
+template<int REGS>
+__device__ __forceinline__ void regs_shrink() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
+}
 constexpr uint32_t V2_ACC_COLS = 3 * TN;
 template<int K>
 constexpr int V2_STAGES = K == 4 ? 8 : 4; // 128 KB of right tiles
@@ -808,8 +835,31 @@ __device__ __forceinline__ void expand_left_to_tmem(const uint4 (&d)[K / 4], uin
     tc_store_wait();
 }
 
+#define V2_ROLE_CONTEXT \
+    uint32_t fresh; \
+    asm volatile("mov.u32 %0, 0;" : "=r"(fresh)); \
+    const uint32_t tmem = *(volatile uint32_t*)&tmem_base_slot + fresh; \
+    const int cols = p.cols; \
+    const int ntiles = p.ntiles; \
+    const int mpairs = p.mtiles; \
+    const long long item0 = p.items * (blockIdx.x + fresh) / gridDim.x; \
+    const int nitems = (int)(p.items * (blockIdx.x + fresh + 1) / gridDim.x - item0); \
+    const uint32_t s_b = ((smem_u32(smem_raw) + fresh) + 1023u) & ~1023u; \
+    const uint32_t s_packed = s_b + NS * KA * ATOM_BYTES; \
+    const uint32_t bar_stage_full = smem_u32(&bars[0]) + fresh; \
+    const uint32_t bar_stage_free = bar_stage_full + 8 * NS; \
+    const uint32_t bar_packed_full = bar_stage_free + 8 * NS; \
+    const uint32_t bar_packed_free = bar_packed_full + 8 * NP; \
+    const uint32_t bar_acc_full = bar_packed_free + 8 * NP; \
+    const uint32_t bar_acc_drained = bar_acc_full + 48; \
+    const uint32_t bar_left_full = bar_acc_drained + 48; \
+    Item it; \
+    it.decode(item0, p.rows, mpairs); \
+    (void)tmem, (void)cols, (void)ntiles, (void)s_b, (void)s_packed, (void)bar_stage_full, (void)bar_stage_free, (void)bar_packed_full, \
+        (void)bar_packed_free, (void)bar_acc_full, (void)bar_acc_drained, (void)bar_left_full;
+
 template<int K, bool NODUPES, bool CT>
-__global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArgs p) {
+__global__ void __maxnreg__(V2_REGS_LAUNCH<K>) search_mma2_kernel(const MmaArgs p) {
     constexpr int KA = K / 4;
     constexpr int NS = V2_STAGES<K>;
     constexpr int NA = V2_LEFT_BUFFERS<K>;
@@ -827,40 +877,26 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
-    const int cols = p.cols;
-    const int ntiles = p.ntiles;
-    const int mpairs = p.mtiles; // here: ceil(cols / 256)
-    const long long item0 = p.items * blockIdx.x / gridDim.x;
-    const int nitems = (int)(p.items * (blockIdx.x + 1) / gridDim.x - item0);
-
-    const uint32_t s_b = (smem_u32(smem_raw) + 1023u) & ~1023u; // + stage * KA * ATOM_BYTES
-    const uint32_t s_packed = s_b + NS * KA * ATOM_BYTES;
-    const uint32_t bar_stage_full = smem_u32(&bars[0]);
-    const uint32_t bar_stage_free = bar_stage_full + 8 * NS;
-    const uint32_t bar_packed_full = bar_stage_free + 8 * NS;
-    const uint32_t bar_packed_free = bar_packed_full + 8 * NP;
-    const uint32_t bar_acc_full = bar_packed_free + 8 * NP;
-    const uint32_t bar_acc_drained = bar_acc_full + 48; // + 8 * (2 * accumulator + half)
-    const uint32_t bar_left_full = bar_acc_drained + 48;
 
     if (tid == 0) {
+        const uint32_t bar0 = smem_u32(&bars[0]);
         s_watch.flag = p.timeout_flag;
         s_watch.timeout_ns = p.timeout_ns;
         s_watch.abort = 0;
         for (int s = 0; s < NS; ++s) {
-            mbar_init(bar_stage_full + 8 * s, TN);
-            mbar_init(bar_stage_free + 8 * s, 2);
+            mbar_init(bar0 + 8 * s, TN); // stage full
+            mbar_init(bar0 + 8 * (NS + s), 2); // stage free
         }
         for (int s = 0; s < NP; ++s) {
-            mbar_init(bar_packed_full + 8 * s, 1);
-            mbar_init(bar_packed_free + 8 * s, TN);
+            mbar_init(bar0 + 8 * (2 * NS + s), 1); // packed full
+            mbar_init(bar0 + 8 * (2 * NS + NP + s), TN); // packed free
         }
         for (int a = 0; a < 6; ++a) {
-            mbar_init(bar_acc_full + 8 * a, 1);
-            mbar_init(bar_acc_drained + 8 * a, TM);
+            mbar_init(bar0 + 8 * (2 * NS + 2 * NP + a), 1); // accumulator full
+            mbar_init(bar0 + 8 * (2 * NS + 2 * NP + 6 + a), TM); // accumulator drained
         }
         for (int b = 0; b < NA; ++b)
-            mbar_init(bar_left_full + 8 * b, 2 * TM);
+            mbar_init(bar0 + 8 * (2 * NS + 2 * NP + 12 + b), 2 * TM); // left full
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -871,12 +907,18 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = tmem_base_slot;
 
-    Item it;
-    it.decode(item0, p.rows, mpairs);
-
-    if (warp == 12 || warp == 13) {
+    // Each role re-balances the registers and only then derives what it needs, inside its own branch: ptxas
+    // allocates a region after a join of branches with different setmaxnreg values for the smallest of them, and
+    // it keeps a value in ONE register for its whole life, so anything computed before the split and used after
+    // it would have to sit in the registers of the smallest role. `fresh` is an opaque zero that keeps the
+    // compiler from hoisting the common expressions back above the split.
+    if (warp >= 12) {
+        regs_shrink<V2_REGS_ISSUER<K>>();
+        V2_ROLE_CONTEXT
+    if (warp == 15) {
+        // the fourth warp of the issuer / loader warpgroup: only there because setmaxnreg works on warpgroups
+    } else if (warp == 12 || warp == 13) {
         // ---- MMA issuers: warp 12 + h issues the MMAs of left half h (whole warp, one elected lane).
         //      Two issuers because the issue loop's own latency, not the tensor pipe, bounds a single one. ----
         {
@@ -945,8 +987,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
                 it.next(p.rows, mpairs);
             }
         }
+    }
     } else if (warp >= 8) {
         // ---- producers ----
+        regs_shrink<V2_REGS_PRODUCER<K>>();
+        V2_ROLE_CONTEXT
         const int r = tid - 2 * TM;
         const int total = nitems * ntiles;
         int t = 0;
@@ -972,6 +1017,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) search_mma2_kernel(const MmaArg
         }
     } else {
         // ---- epilogue: half h = warps 4h..4h+3, thread = TMEM lane = left pixel 256 mp + 128 h + lane ----
+        regs_grow<V2_REGS_EPILOGUE<K>>();
+        V2_ROLE_CONTEXT
         const int h = warp >> 2;
         const int lane128 = tid & (TM - 1);
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
@@ -1075,7 +1122,7 @@ teardown:
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*(volatile uint32_t*)&tmem_base_slot), "r"(512u) : "memory");
     }
 }
 
