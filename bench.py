@@ -47,7 +47,7 @@ WORKLOAD = ("2x33 uint8 2048x1536, LIMITED, thr 0.96, min_var 2.0, subpixel_step
 CONFIG = {
     "workload": WORKLOAD,
     "frames_per_gpu_per_step": FRAMES,
-    "sharding": "frame-sharded, one process per GPU, no data-path collective",
+    "sharding": "frame-sharded, one process per GPU, no data-path collective; the frames of a step are one bicos_b200_match_batch",
     "l2": f"inputs larger than L2 ({FRAMES} x 208 MB per GPU per step); no explicit flush",
     "reference_arm_sample": "a bounded row sample of one stereo stack per step (cost is linear in rows), see cpu_baseline.sample",
 }
@@ -281,7 +281,16 @@ def main():
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # fewer ranks than visible GPUs: spread them over the node's PCIe tree (the end-to-end path is bound by the
+    # host link, which neighbouring GPUs share); BICOS_BENCH_DEVICES=first keeps LOCAL_RANK = ordinal
+    from libbicos_b200 import topology
+
+    if os.environ.get("BICOS_BENCH_DEVICES", "") == "first":
+        devices, device_policy = list(range(world)), "LOCAL_RANK = ordinal (BICOS_BENCH_DEVICES=first)"
+    else:
+        devices, device_policy = topology.pick_devices(world)
+    local = devices[local_rank]
     torch.cuda.set_device(local)
     all_cpus = os.sched_getaffinity(0)
     affinity = bind_to_gpu_cpus(local)
@@ -314,6 +323,11 @@ def main():
     torch.cuda.synchronize()
 
     def step():
+        # throughput mode: the FRAMES stereo stacks of a step as one batch (bicos_b200_match_batch: frame f + 1's
+        # transform + search beside frame f's refine; the current stream is joined before and after)
+        h.match_batch(frames, cfg, outs=outs)
+
+    def step_serial():
         for (l, r), out in zip(frames, outs):
             h.match(l, r, cfg, out=out)
 
@@ -434,21 +448,38 @@ def main():
             traffic = json.load(f)
     except OSError:
         pass
+    # the same frames one match after the other on one stream: every kernel alone on the GPU
+    h.set_overlap(False)
+    for _ in range(2):
+        step_serial()
+    torch.cuda.synchronize()
+    h.set_profiling(True)
+    ev0.record()
+    for _ in range(5):
+        step_serial()
+    ev1.record()
+    alone_ms, alone_n = h.stage_times()
+    h.set_profiling(False)
+    serial_ms_per_match = ev0.elapsed_time(ev1) / (5 * FRAMES)
+    a_tr, a_se, a_re = (1e-3 * v / max(alone_n, 1) for v in alone_ms)
+
     # the other engine on the same frames, for the record (stage timer of the handle)
     engine = lb.search_engine()
     tensor = engine != "popc"  # K = 4, 2048 columns: inside the tensor-core engine's range
     lb.set_search_engine("popc" if tensor else "tensor")
     for _ in range(2):
-        step()
+        step_serial()
     torch.cuda.synchronize()
     h.set_profiling(True)
     for _ in range(3):
-        step()
+        step_serial()
     other_ms, other_n = h.stage_times()
     h.set_profiling(False)
     lb.set_search_engine(engine)
+    h.set_overlap(True)
     t_other = 1e-3 * other_ms[1] / max(other_n, 1)
     t_popc, t_mma = (t_other, t_se) if tensor else (t_se, t_other)
+    t_mma_alone = a_se if tensor else t_other
 
     popc_issued = COLS * px * 3  # the popc kernel's carry-save form: 3 POPC per 128-bit pair
     popc_line = {
@@ -472,6 +503,11 @@ def main():
         "peak_kind": "dense int8 tensor rate (tcgen05 kind::i8)", "peak_source": int8_src, "ms_per_launch": t_mma * 1e3,
         "achieved_executed": mma_ops / t_mma / 1e12, "frac_executed": mma_ops / t_mma / 1e12 / int8_peak,
         "executed_over_algorithmic": dirs,
+        # ms_per_launch / achieved / frac are the timed region's: there the kernel shares its SMs with the previous frame's
+        # refine CTAs (match_batch). The same kernel with the GPU to itself (one match after the other, same run):
+        "alone": {"ms_per_launch": t_mma_alone * 1e3, "achieved": mma_ops_once / t_mma_alone / 1e12,
+                  "frac": mma_ops_once / t_mma_alone / 1e12 / int8_peak,
+                  "achieved_executed": mma_ops / t_mma_alone / 1e12, "frac_executed": mma_ops / t_mma_alone / 1e12 / int8_peak},
         "smem_frac": smem_bytes / t_mma / (128.0 * 148 * sm_max * 1e6),
         # SURVEY 8d scores the search in popc32 (S = W * P * K) against the POPC pipe, the bound of a popcount kernel:
         # the same algorithmic work over this engine's time, for comparison with that table
@@ -536,9 +572,15 @@ def main():
         "config": CONFIG,
         "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": FRAMES * 2 * N_IMAGES * px,
                 "d2h_bytes_per_step": FRAMES * px * 8, "ms_per_step": e2e_ms, "matches_device_path": same, "host_affinity": affinity,
+                "devices": devices, "device_policy": device_policy,
                 "api": f"bicos_b200_match_host_begin/_end, {inflight} frames in flight (pinned host stacks -> host disparity + corrmap)"},
         "gpu_launches": launches,
-        "stage_ms_per_match": {"transform_x2": t_tr * 1e3, "search": t_se * 1e3, "refine": t_re * 1e3},
+        "stage_ms_per_match": {"transform_x2": t_tr * 1e3, "search": t_se * 1e3, "refine": t_re * 1e3,
+                               "note": "CUDA events around each stage on its own stream inside the timed region; search and refine of "
+                                       "consecutive frames overlap there, so the stages add up to more than ms_per_match"},
+        "serial": {"ms_per_match": serial_ms_per_match, "mpx_per_s": px / serial_ms_per_match / 1e3,
+                   "stage_ms_per_match": {"transform_x2": a_tr * 1e3, "search": a_se * 1e3, "refine": a_re * 1e3},
+                   "note": "bicos_b200_match frame after frame on one stream (round 1's timed region): every kernel alone on the GPU"},
         "roofline": roofline, "roofline_other": roofline_other, "cpu_baseline": cpu_baseline, "parity": parity,
         "row_sharded": row_sharded, "reference_cuda": reference_cuda, "clocks": clocks,
     }

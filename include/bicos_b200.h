@@ -144,6 +144,26 @@ int bicos_b200_match(bicos_b200_handle h, const void* const* planes0, const void
                      const bicos_b200_config* cfg, void* disparity, size_t disparity_pitch_bytes,
                      void* corrmap, size_t corrmap_pitch_bytes, void* stream);
 
+/* Throughput mode: `count` independent stereo stacks of one shape, type and configuration (BASELINE.json's batch
+ * configuration). planes0[f] / planes1[f] are the n plane pointers of frame f, disparity[f] / corrmap[f] its outputs
+ * (corrmap may be NULL, or hold NULL entries). Same results as `count` calls of bicos_b200_match, but the frames
+ * flow through two internal streams: the transform + search of frame f + 1 (tensor cores) runs beside the
+ * postfilter + refine of frame f (FP32 pipe), which the register budget of the search kernel is laid out for.
+ * `stream` is joined on both sides: earlier work on it completes before the first frame starts, and it continues
+ * only after the last frame is complete. The reference has no batch entry point: its callers loop over
+ * BICOS::match (src/cli.cpp:188-215 per stack). */
+int bicos_b200_match_batch(bicos_b200_handle h, int count, const void* const* const* planes0,
+                           const void* const* const* planes1, int n, int rows, int cols, size_t pitch_bytes,
+                           int depth, const bicos_b200_config* cfg, void* const* disparity,
+                           size_t disparity_pitch_bytes, void* const* corrmap, size_t corrmap_pitch_bytes,
+                           void* stream);
+
+/* Whether bicos_b200_match and bicos_b200_match_batch may run the search of one unit (row band, frame) beside the
+ * refine of the previous one on the handle's two internal streams (default: yes). 0 = every kernel of a match one
+ * after the other on the caller's stream, as in the reference (src/impl/cuda.cu:148-458): same results, used for
+ * A/B timing and when a caller wants nothing enqueued outside its own stream. */
+int bicos_b200_set_overlap(bicos_b200_handle h, int enabled);
+
 /* Host-resident variant (what pybicos' BICOS_Match needs): dense host images in, dense host
  * results out; uploads, runs bicos_b200_match and downloads through the handle's pinned
  * staging buffers, then synchronises. */

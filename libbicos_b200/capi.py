@@ -23,7 +23,7 @@ EXPORTS = (
     "bicos_b200_last_error", "bicos_b200_device_count", "bicos_b200_create", "bicos_b200_destroy",
     "bicos_b200_descriptor_words", "bicos_b200_disparity_type", "bicos_b200_corrmap_type",
     "bicos_b200_transform", "bicos_b200_search", "bicos_b200_refine", "bicos_b200_match",
-    "bicos_b200_match_host", "bicos_b200_match_host_begin", "bicos_b200_match_host_end", "bicos_b200_match_rows", "bicos_b200_synchronize",
+    "bicos_b200_match_batch", "bicos_b200_set_overlap", "bicos_b200_match_host", "bicos_b200_match_host_begin", "bicos_b200_match_host_end", "bicos_b200_match_rows", "bicos_b200_synchronize",
     "bicos_b200_kernel_launches", "bicos_b200_set_profiling", "bicos_b200_stage_times",
     "bicos_b200_shared_alloc", "bicos_b200_shared_open", "bicos_b200_shared_close", "bicos_b200_shared_free",
     "bicos_b200_set_search_engine", "bicos_b200_get_search_engine", "bicos_b200_last_search_kernel",
@@ -115,6 +115,8 @@ def lib():
         L.bicos_b200_search.argtypes = [vp, vp, vp, i, i, i, sz, i, vp, vp, vp, vp, vp]
         L.bicos_b200_refine.argtypes = [vp, pp, pp, i, i, i, sz, i, cfgp, vp, vp, vp, vp, vp, vp, sz, vp, sz, vp]
         L.bicos_b200_match.argtypes = [vp, pp, pp, i, i, i, sz, i, cfgp, vp, sz, vp, sz, vp]
+        L.bicos_b200_match_batch.argtypes = [vp, i, vp, vp, i, i, i, sz, i, cfgp, vp, sz, vp, sz, vp]
+        L.bicos_b200_set_overlap.argtypes = [vp, i]
         L.bicos_b200_match_rows.argtypes = [vp, pp, pp, i, i, i, sz, i, cfgp, i, i, vp, sz, vp, sz, vp]
         L.bicos_b200_match_host.argtypes = [vp, pp, pp, i, i, i, i, cfgp, vp, vp]
         L.bicos_b200_match_host_begin.argtypes = [vp, pp, pp, i, i, i, i, cfgp, vp, vp]
@@ -355,6 +357,42 @@ class Handle:
                                                int(rows_range[0]), int(rows_range[1]), *args))
         return disp, corr
 
+    def match_batch(self, frames, cfg: Config, outs=None):
+        """Throughput mode (bicos_b200_match_batch): `frames` = [(stack0, stack1), ...] of one shape and dtype,
+        device-resident; returns [(disparity, corrmap), ...]. Frame f + 1's transform + search run beside frame f's
+        refine on two internal streams; the current stream is joined before and after."""
+        if not frames:
+            return []
+        infos = [(self._stack_info(a), self._stack_info(b)) for a, b in frames]
+        first = infos[0][0][1:]
+        for ia, ib in infos:
+            if ia[1:] != first or ib[1:] != first:
+                raise BicosError("all stacks of a batch must agree in length, size, type and pitch")
+        _, n, rows, cols, pitch, depth = infos[0][0]
+        device = frames[0][0].device
+        ccfg = cfg.to_c()
+        if outs is None:
+            outs = [self._outputs(cfg, rows, cols, device)[1:] for _ in frames]
+        else:
+            if len(outs) != len(frames):
+                raise BicosError("outs must hold one (disparity, corrmap) pair per frame")
+            outs = [self._check_out(ccfg, o, rows, cols, device) for o in outs]
+        count = len(frames)
+        p0 = (ctypes.c_void_p * count)(*[ctypes.cast(ia[0], ctypes.c_void_p) for ia, _ in infos])
+        p1 = (ctypes.c_void_p * count)(*[ctypes.cast(ib[0], ctypes.c_void_p) for _, ib in infos])
+        disp = (ctypes.c_void_p * count)(*[d.data_ptr() for d, _ in outs])
+        has_corr = outs[0][1] is not None
+        corr = (ctypes.c_void_p * count)(*[c.data_ptr() for _, c in outs]) if has_corr else None
+        d0, c0 = outs[0]
+        for d, c in outs:
+            if d.stride(0) != d0.stride(0) or (has_corr and c.stride(0) != c0.stride(0)):
+                raise BicosError("all outputs of a batch must share one pitch")
+        _check(lib().bicos_b200_match_batch(
+            self._h, count, p0, p1, n, rows, cols, pitch, depth, ctypes.byref(ccfg), disp, d0.stride(0) * d0.element_size(),
+            corr, c0.stride(0) * c0.element_size() if has_corr else 0, self._stream()))
+        self._batch_keepalive = (infos, p0, p1, disp, corr)
+        return list(outs)
+
     def match_raw(self, stack0, stack1, cfg: Config, disp_ptr: int, disp_pitch: int, corr_ptr: Optional[int],
                   corr_pitch: int) -> None:
         """Device-resident match writing to raw device addresses (e.g. rows of a peer-mapped image
@@ -421,6 +459,10 @@ class Handle:
     def match_host_end(self) -> None:
         _check(lib().bicos_b200_match_host_end(self._h))
         self._host_keepalive = None
+
+    def set_overlap(self, enabled: bool) -> None:
+        """False: every kernel of a match one after the other on the caller's stream (bicos_b200_set_overlap)."""
+        _check(lib().bicos_b200_set_overlap(self._h, int(enabled)))
 
     def set_profiling(self, enabled: bool) -> None:
         """Record CUDA events around the three stages of every match (resets the accumulators)."""

@@ -301,9 +301,15 @@ struct bicos_b200_handle_s {
     // host-buffer pipeline (bicos_b200_match_host): upload / compute / download streams
     cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[MAX_BANDS] = {}, ev_done[MAX_BANDS] = {};
+    // two-stream pipeline of bicos_b200_match_batch: transform + search of unit u + 1 beside the refine of unit u
+    DeviceBuffer keys_b; // second set of key arrays (unit parity)
+    bool overlap = true; // bicos_b200_set_overlap
+    cudaStream_t p_search = nullptr, p_refine = nullptr;
+    cudaEvent_t p_start = nullptr, p_done = nullptr, p_searched[2] = {}, p_refined[2] = {};
     // optional per-stage timing (bicos_b200_set_profiling)
     bool profiling = false;
-    std::vector<cudaEvent_t> prof_events; // N_STAGES + 1 events per recorded match
+    std::vector<cudaEvent_t> prof_events; // a (begin, end) event pair per recorded stage, stage index in prof_stage
+    std::vector<int> prof_stage;
     size_t prof_used = 0;
     double stage_ms[N_STAGES] = { 0, 0, 0 };
     long long stage_count = 0;
@@ -369,28 +375,41 @@ int prepare_steps(bicos_b200_handle h, float step, cudaStream_t stream) {
     return 0;
 }
 
-int prof_mark(bicos_b200_handle h, cudaStream_t stream) {
+// Stage timing: an event before and after a stage on the stream it runs on (the stages of a match may run on
+// different streams, bicos_b200_match_batch), folded into stage_ms by prof_collect.
+int prof_event(bicos_b200_handle h, int stage, cudaStream_t stream) {
     if (!h->profiling)
         return 0;
     if (h->prof_used == h->prof_events.size()) {
         cudaEvent_t e;
         CU(cudaEventCreate(&e));
         h->prof_events.push_back(e);
+        h->prof_stage.push_back(0);
     }
+    h->prof_stage[h->prof_used] = stage;
     CU(cudaEventRecord(h->prof_events[h->prof_used++], stream));
     return 0;
 }
 
-// fold all completed (N_STAGES + 1)-event groups into stage_ms; requires the work to be finished
+struct StageTimer {
+    bicos_b200_handle h;
+    int stage;
+    cudaStream_t stream;
+    int rc;
+    StageTimer(bicos_b200_handle h_, int stage_, cudaStream_t stream_): h(h_), stage(stage_), stream(stream_) {
+        rc = prof_event(h, stage, stream);
+    }
+    int end() {
+        return rc ? rc : prof_event(h, stage, stream);
+    }
+};
+
+// fold all completed (begin, end) pairs into stage_ms; requires the work to be finished
 int prof_collect(bicos_b200_handle h) {
-    const size_t group = N_STAGES + 1;
-    for (size_t g = 0; g + group <= h->prof_used; g += group) {
-        for (int st = 0; st < N_STAGES; ++st) {
-            float ms = 0.f;
-            CU(cudaEventElapsedTime(&ms, h->prof_events[g + st], h->prof_events[g + st + 1]));
-            h->stage_ms[st] += ms;
-        }
-        h->stage_count += 1;
+    for (size_t g = 0; g + 2 <= h->prof_used; g += 2) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->prof_events[g], h->prof_events[g + 1]));
+        h->stage_ms[h->prof_stage[g]] += ms;
     }
     h->prof_used = 0;
     return 0;
@@ -484,6 +503,120 @@ int do_refine(
     return 0;
 }
 
+// One unit of work of the path: rows [row_begin, row_end) of one stereo stack, with the output rows it writes.
+struct Unit {
+    PlaneTable t0, t1; // plane pointers already advanced to row_begin
+    int nrows = 0;
+    char* disp_rows = nullptr;
+    char* corr_rows = nullptr;
+};
+
+struct MatchShape {
+    int n, cols, K, depth, flags;
+    size_t pitch_bytes, disparity_pitch, corrmap_pitch;
+    const bicos_b200_config* cfg;
+};
+
+int make_unit(Unit& u, const void* const* planes0, const void* const* planes1, const MatchShape& sh, int row_begin, int row_end,
+              void* disparity, void* corrmap) {
+    if (int rc = fill_table(u.t0, planes0, sh.n, (size_t)row_begin * sh.pitch_bytes))
+        return rc;
+    if (int rc = fill_table(u.t1, planes1, sh.n, (size_t)row_begin * sh.pitch_bytes))
+        return rc;
+    u.nrows = row_end - row_begin;
+    u.disp_rows = static_cast<char*>(disparity) + (size_t)row_begin * sh.disparity_pitch;
+    u.corr_rows = corrmap ? static_cast<char*>(corrmap) + (size_t)row_begin * sh.corrmap_pitch : nullptr;
+    return 0;
+}
+
+// stages 1 + 2 of a unit: both descriptor transforms and the search, keys into `keys`
+int enqueue_search_stage(bicos_b200_handle h, const Unit& u, const MatchShape& sh, uint32_t* keys, cudaStream_t stream) {
+    const size_t dpw = desc_pitch_for(sh.cols, sh.K);
+    const size_t px = (size_t)u.nrows * sh.cols;
+    uint32_t* d0 = static_cast<uint32_t*>(h->desc0.ptr);
+    uint32_t* d1 = static_cast<uint32_t*>(h->desc1.ptr);
+    const int is_u16 = sh.depth == BICOS_B200_16U;
+    {
+        Range nvtx("bicos_b200::transform x2");
+        StageTimer timer(h, 0, stream);
+        CU(launch_transform(u.t0, sh.n, u.nrows, sh.cols, sh.pitch_bytes, is_u16, mode_is_full(sh.cfg->mode), sh.K, d0, dpw, stream));
+        CU(launch_transform(u.t1, sh.n, u.nrows, sh.cols, sh.pitch_bytes, is_u16, mode_is_full(sh.cfg->mode), sh.K, d1, dpw, stream));
+        h->launches += 2;
+        if (int rc = timer.end())
+            return rc;
+    }
+    Range nvtx("bicos_b200::search");
+    StageTimer timer(h, 1, stream);
+    KeyArrays ka = split_keys(keys, px, sh.flags);
+    if (search_needs_prefill(sh.K, sh.cols)) // the popcount engine merges with atomicMin; the tensor-core engine stores every key
+        CU(cudaMemsetAsync(keys, 0xFF, px * sizeof(uint32_t) * key_arrays(sh.flags), stream));
+    // descriptors of our own transform: 4n - 6 or n^2 - 2n + 3 bits, never all 32 K, so the top bit is free
+    CU(launch_search(d0, d1, sh.K, u.nrows, sh.cols, dpw, sh.flags, ka.fwd_first, ka.fwd_last, ka.rev_first, ka.rev_last, stream, true));
+    h->launches += 1;
+    return timer.end();
+}
+
+// stages 4 + 3 of a unit: postfilter and NXC refinement from `keys` into the unit's output rows
+int enqueue_refine_stage(bicos_b200_handle h, const Unit& u, const MatchShape& sh, uint32_t* keys, cudaStream_t stream) {
+    Range nvtx("bicos_b200::postfilter+refine");
+    StageTimer timer(h, 2, stream);
+    KeyArrays ka = split_keys(keys, (size_t)u.nrows * sh.cols, sh.flags);
+    if (int rc = do_refine(h, u.t0, u.t1, sh.n, u.nrows, sh.cols, sh.pitch_bytes, sh.depth, sh.cfg, ka.fwd_first, ka.fwd_last, ka.rev_first,
+                           ka.rev_last, nullptr, u.disp_rows, sh.disparity_pitch, u.corr_rows, sh.corrmap_pitch, stream))
+        return rc;
+    return timer.end();
+}
+
+int validate_match(const void* const* planes0, const void* const* planes1, int n, int rows, int cols, size_t pitch_bytes, int depth,
+                   const bicos_b200_config* cfg, const void* disparity, MatchShape& sh) {
+    int K = 0;
+    if (int rc = validate_common(n, rows, cols, depth, cfg, &K))
+        return rc;
+    if (!planes0 || !planes1 || !disparity)
+        return fail(BICOS_B200_ERR_INVALID, "null argument");
+    if (pitch_bytes < (size_t)cols * depth_bytes(depth))
+        return fail(BICOS_B200_ERR_INVALID, "pitch smaller than a row");
+    sh.n = n;
+    sh.cols = cols;
+    sh.K = K;
+    sh.depth = depth;
+    sh.flags = search_flags(cfg);
+    sh.pitch_bytes = pitch_bytes;
+    sh.cfg = cfg;
+    return 0;
+}
+
+int reserve_workspace(bicos_b200_handle h, const MatchShape& sh, int max_unit_rows, bool second_keys) {
+    const size_t dpw = desc_pitch_for(sh.cols, sh.K);
+    CU(h->desc0.reserve(dpw * max_unit_rows * sizeof(uint32_t)));
+    CU(h->desc1.reserve(dpw * max_unit_rows * sizeof(uint32_t)));
+    // key arrays, contiguous so that one memset initialises them: fwd_first, then fwd_last
+    // (NODUPES), rev_first (CONSISTENCY), rev_last (both)
+    const size_t key_bytes = (size_t)max_unit_rows * sh.cols * sizeof(uint32_t) * key_arrays(sh.flags);
+    CU(h->keys.reserve(key_bytes));
+    if (second_keys)
+        CU(h->keys_b.reserve(key_bytes));
+    return 0;
+}
+
+// the handle's workspace is shared by everything enqueued through it: order after its previous user
+int enter_workspace(bicos_b200_handle h, cudaStream_t stream) {
+    if (int rc = check_search_timeout())
+        return rc;
+    if (h->has_last && h->last_stream != stream)
+        CU(cudaStreamWaitEvent(stream, h->ev_last, 0));
+    return 0;
+}
+
+int leave_workspace(bicos_b200_handle h, cudaStream_t stream) {
+    if (!h->ev_last)
+        CU(cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming));
+    CU(cudaEventRecord(h->ev_last, stream));
+    h->last_stream = stream;
+    h->has_last = true;
+    return 0;
+}
+
 int do_match(
     bicos_b200_handle h,
     const void* const* planes0,
@@ -502,76 +635,74 @@ int do_match(
     size_t corrmap_pitch,
     cudaStream_t stream
 ) {
-    int K = 0;
-    if (int rc = validate_common(n, rows, cols, depth, cfg, &K))
+    MatchShape sh {};
+    if (int rc = validate_match(planes0, planes1, n, rows, cols, pitch_bytes, depth, cfg, disparity, sh))
         return rc;
-    if (!planes0 || !planes1 || !disparity)
-        return fail(BICOS_B200_ERR_INVALID, "null argument");
     if (row_begin < 0 || row_end > rows || row_begin >= row_end)
         return fail(BICOS_B200_ERR_INVALID, "bad row range [%d, %d) of %d", row_begin, row_end, rows);
-    if (pitch_bytes < (size_t)cols * depth_bytes(depth))
-        return fail(BICOS_B200_ERR_INVALID, "pitch smaller than a row");
-
+    sh.disparity_pitch = disparity_pitch;
+    sh.corrmap_pitch = corrmap_pitch;
     Range nvtx_match("bicos_b200::match");
-    const int nrows = row_end - row_begin;
-    PlaneTable t0, t1;
-    if (int rc = fill_table(t0, planes0, n, (size_t)row_begin * pitch_bytes))
+    Unit u;
+    if (int rc = make_unit(u, planes0, planes1, sh, row_begin, row_end, disparity, corrmap))
         return rc;
-    if (int rc = fill_table(t1, planes1, n, (size_t)row_begin * pitch_bytes))
+    if (int rc = enter_workspace(h, stream))
         return rc;
+    if (int rc = reserve_workspace(h, sh, u.nrows, false))
+        return rc;
+    uint32_t* keys = static_cast<uint32_t*>(h->keys.ptr);
+    if (int rc = enqueue_search_stage(h, u, sh, keys, stream))
+        return rc;
+    if (int rc = enqueue_refine_stage(h, u, sh, keys, stream))
+        return rc;
+    h->stage_count += 1;
+    return leave_workspace(h, stream);
+}
 
-    if (int rc = check_search_timeout())
-        return rc;
-    const int flags = search_flags(cfg);
-    const size_t dpw = desc_pitch_for(cols, K);
-    const size_t px = (size_t)nrows * cols;
-    if (h->has_last && h->last_stream != stream)
-        CU(cudaStreamWaitEvent(stream, h->ev_last, 0)); // the previous match still owns the workspace
-    CU(h->desc0.reserve(dpw * nrows * sizeof(uint32_t)));
-    CU(h->desc1.reserve(dpw * nrows * sizeof(uint32_t)));
-    // key arrays, contiguous so that one memset initialises them: fwd_first, then fwd_last
-    // (NODUPES), rev_first (CONSISTENCY), rev_last (both)
-    const int n_keys = key_arrays(flags);
-    CU(h->keys.reserve(px * sizeof(uint32_t) * n_keys));
-
-    uint32_t* d0 = static_cast<uint32_t*>(h->desc0.ptr);
-    uint32_t* d1 = static_cast<uint32_t*>(h->desc1.ptr);
-    const int is_u16 = depth == BICOS_B200_16U;
-    if (int rc = prof_mark(h, stream))
-        return rc;
-    {
-        Range nvtx("bicos_b200::transform x2");
-        CU(launch_transform(t0, n, nrows, cols, pitch_bytes, is_u16, mode_is_full(cfg->mode), K, d0, dpw, stream));
-        CU(launch_transform(t1, n, nrows, cols, pitch_bytes, is_u16, mode_is_full(cfg->mode), K, d1, dpw, stream));
-        h->launches += 2;
+// Units through two internal streams: transform + search of unit u + 1 (tensor pipe; high-priority stream, so that its
+// one-CTA-per-SM grid is placed as soon as an SM has room) beside postfilter + refine of unit u (FP32 pipe). The
+// search kernel holds 40 K of an SM's 64 K registers (search_mma.cu, setmaxnreg), which leaves room for one refine
+// CTA; key arrays alternate between two buffers, descriptors need one (both their producer and their consumer are on
+// the search stream). `stream` is joined on both sides: everything enqueued before this call is complete before the
+// first unit starts, and `stream` continues after the last refine.
+int run_pipeline(bicos_b200_handle h, const std::vector<Unit>& units, const MatchShape& sh, cudaStream_t stream) {
+    if (!h->p_search) {
+        int least = 0, greatest = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CU(cudaStreamCreateWithPriority(&h->p_search, cudaStreamNonBlocking, greatest));
+        CU(cudaStreamCreateWithPriority(&h->p_refine, cudaStreamNonBlocking, least));
+        for (cudaEvent_t* e: { &h->p_start, &h->p_done, &h->p_searched[0], &h->p_searched[1], &h->p_refined[0], &h->p_refined[1] })
+            CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
-    if (int rc = prof_mark(h, stream))
+    if (int rc = enter_workspace(h, stream))
         return rc;
-
-    KeyArrays ka = split_keys(static_cast<uint32_t*>(h->keys.ptr), px, flags);
-    if (search_needs_prefill(K, cols)) // the popcount engine merges with atomicMin; the tensor-core engine stores every key
-        CU(cudaMemsetAsync(h->keys.ptr, 0xFF, px * sizeof(uint32_t) * n_keys, stream));
-    // descriptors of our own transform: 4n - 6 or n^2 - 2n + 3 bits, never all 32 K, so the top bit is free
-    {
-        Range nvtx("bicos_b200::search");
-        CU(launch_search(d0, d1, K, nrows, cols, dpw, flags, ka.fwd_first, ka.fwd_last, ka.rev_first, ka.rev_last, stream, true));
-        h->launches += 1;
+    int max_rows = 0;
+    for (const Unit& u: units)
+        max_rows = u.nrows > max_rows ? u.nrows : max_rows;
+    if (int rc = reserve_workspace(h, sh, max_rows, true))
+        return rc;
+    uint32_t* const keys[2] = { static_cast<uint32_t*>(h->keys.ptr), static_cast<uint32_t*>(h->keys_b.ptr) };
+    if (sh.cfg->subpixel_step >= 0 && has_thr(sh.cfg))
+        if (int rc = prepare_steps(h, sh.cfg->subpixel_step, stream)) // before the fork: may synchronise `stream`
+            return rc;
+    CU(cudaEventRecord(h->p_start, stream));
+    CU(cudaStreamWaitEvent(h->p_search, h->p_start, 0));
+    CU(cudaStreamWaitEvent(h->p_refine, h->p_start, 0));
+    for (size_t i = 0; i < units.size(); ++i) {
+        const int slot = (int)(i & 1);
+        if (i >= 2)
+            CU(cudaStreamWaitEvent(h->p_search, h->p_refined[slot], 0)); // the refine that read this key buffer
+        if (int rc = enqueue_search_stage(h, units[i], sh, keys[slot], h->p_search))
+            return rc;
+        CU(cudaEventRecord(h->p_searched[slot], h->p_search));
+        CU(cudaStreamWaitEvent(h->p_refine, h->p_searched[slot], 0));
+        if (int rc = enqueue_refine_stage(h, units[i], sh, keys[slot], h->p_refine))
+            return rc;
+        CU(cudaEventRecord(h->p_refined[slot], h->p_refine));
     }
-    if (int rc = prof_mark(h, stream))
-        return rc;
-
-    char* disp_rows = static_cast<char*>(disparity) + (size_t)row_begin * disparity_pitch;
-    char* corr_rows = corrmap ? static_cast<char*>(corrmap) + (size_t)row_begin * corrmap_pitch : nullptr;
-    Range nvtx_refine("bicos_b200::postfilter+refine");
-    if (int rc = do_refine(h, t0, t1, n, nrows, cols, pitch_bytes, depth, cfg, ka.fwd_first, ka.fwd_last, ka.rev_first, ka.rev_last,
-                           nullptr, disp_rows, disparity_pitch, corr_rows, corrmap_pitch, stream))
-        return rc;
-    if (!h->ev_last)
-        CU(cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming));
-    CU(cudaEventRecord(h->ev_last, stream));
-    h->last_stream = stream;
-    h->has_last = true;
-    return prof_mark(h, stream);
+    CU(cudaEventRecord(h->p_done, h->p_refine)); // in stream order after every refine, each after its search
+    CU(cudaStreamWaitEvent(stream, h->p_done, 0));
+    return leave_workspace(h, stream);
 }
 
 } // namespace
@@ -626,6 +757,13 @@ int bicos_b200_destroy(bicos_b200_handle h) {
             cudaEventDestroy(e);
         if (h->ev_last)
             cudaEventDestroy(h->ev_last);
+        h->keys_b.release();
+        for (cudaEvent_t e: { h->p_start, h->p_done, h->p_searched[0], h->p_searched[1], h->p_refined[0], h->p_refined[1] })
+            if (e)
+                cudaEventDestroy(e);
+        for (cudaStream_t st: { h->p_search, h->p_refine })
+            if (st)
+                cudaStreamDestroy(st);
         for (int k = 0; k < PIN_SLOTS; ++k) {
             h->pin_in[k].release();
             if (h->ev_slot[k])
@@ -751,6 +889,35 @@ int bicos_b200_refine(bicos_b200_handle h, const void* const* planes0, const voi
                      static_cast<cudaStream_t>(stream));
 }
 
+// A single match of a large image with the subpixel refine (the FP32-heavy one): as three row bands through the
+// two-stream pipeline, band b + 1's search beside band b's refine. Rows are independent, so the result is the same;
+// measured on the metric configuration: 1.91 against 2.01 ms (2 bands 1.93, 4 bands 1.91; tools/overlap_probe.py).
+// Small images, integer refinement and the popcount engine (which leaves no issue slots free) run as one unit.
+static int match_banded_or_whole(bicos_b200_handle h, const void* const* planes0, const void* const* planes1, int n, int rows,
+                                 int cols, size_t pitch_bytes, int depth, const bicos_b200_config* cfg, void* disparity,
+                                 size_t disparity_pitch, void* corrmap, size_t corrmap_pitch, cudaStream_t stream) {
+    constexpr int BANDS = 3, MIN_BAND_ROWS = 384;
+    MatchShape sh {};
+    if (int rc = validate_match(planes0, planes1, n, rows, cols, pitch_bytes, depth, cfg, disparity, sh))
+        return rc;
+    const bool subpixel = has_thr(cfg) && cfg->subpixel_step >= 0;
+    if (!h->overlap || !subpixel || rows < BANDS * MIN_BAND_ROWS || search_needs_prefill(sh.K, cols) || (sh.K != 4 && sh.K != 8))
+        return do_match(h, planes0, planes1, n, rows, cols, pitch_bytes, depth, cfg, 0, rows, disparity, disparity_pitch, corrmap,
+                        corrmap_pitch, stream);
+    sh.disparity_pitch = disparity_pitch;
+    sh.corrmap_pitch = corrmap_pitch;
+    std::vector<Unit> units(BANDS);
+    for (int b = 0; b < BANDS; ++b)
+        if (int rc = make_unit(units[(size_t)b], planes0, planes1, sh, (int)((long long)rows * b / BANDS),
+                               (int)((long long)rows * (b + 1) / BANDS), disparity, corrmap))
+            return rc;
+    Range nvtx("bicos_b200::match (banded)");
+    if (int rc = run_pipeline(h, units, sh, stream))
+        return rc;
+    h->stage_count += 1;
+    return 0;
+}
+
 int bicos_b200_match(bicos_b200_handle h, const void* const* planes0, const void* const* planes1,
                      int n, int rows, int cols, size_t pitch_bytes, int depth,
                      const bicos_b200_config* cfg, void* disparity, size_t disparity_pitch_bytes,
@@ -758,8 +925,8 @@ int bicos_b200_match(bicos_b200_handle h, const void* const* planes0, const void
     if (!h)
         return fail(BICOS_B200_ERR_INVALID, "null handle");
     DeviceGuard g(h->device);
-    return do_match(h, planes0, planes1, n, rows, cols, pitch_bytes, depth, cfg, 0, rows, disparity,
-                    disparity_pitch_bytes, corrmap, corrmap_pitch_bytes, static_cast<cudaStream_t>(stream));
+    return match_banded_or_whole(h, planes0, planes1, n, rows, cols, pitch_bytes, depth, cfg, disparity,
+                                 disparity_pitch_bytes, corrmap, corrmap_pitch_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int bicos_b200_match_rows(bicos_b200_handle h, const void* const* planes0,
@@ -772,6 +939,47 @@ int bicos_b200_match_rows(bicos_b200_handle h, const void* const* planes0,
     DeviceGuard g(h->device);
     return do_match(h, planes0, planes1, n, rows, cols, pitch_bytes, depth, cfg, row_begin, row_end, disparity,
                     disparity_pitch_bytes, corrmap, corrmap_pitch_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int bicos_b200_match_batch(bicos_b200_handle h, int count, const void* const* const* planes0,
+                           const void* const* const* planes1, int n, int rows, int cols, size_t pitch_bytes,
+                           int depth, const bicos_b200_config* cfg, void* const* disparity,
+                           size_t disparity_pitch_bytes, void* const* corrmap, size_t corrmap_pitch_bytes,
+                           void* stream) {
+    if (!h)
+        return fail(BICOS_B200_ERR_INVALID, "null handle");
+    if (count <= 0 || !planes0 || !planes1 || !disparity)
+        return fail(BICOS_B200_ERR_INVALID, "empty batch or null argument");
+    DeviceGuard g(h->device);
+    MatchShape sh {};
+    std::vector<Unit> units((size_t)count);
+    for (int f = 0; f < count; ++f) {
+        if (int rc = validate_match(planes0[f], planes1[f], n, rows, cols, pitch_bytes, depth, cfg, disparity[f], sh))
+            return rc;
+        sh.disparity_pitch = disparity_pitch_bytes;
+        sh.corrmap_pitch = corrmap_pitch_bytes;
+        if (int rc = make_unit(units[(size_t)f], planes0[f], planes1[f], sh, 0, rows, disparity[f], corrmap ? corrmap[f] : nullptr))
+            return rc;
+    }
+    Range nvtx("bicos_b200::match_batch");
+    if (!h->overlap) {
+        for (int f = 0; f < count; ++f)
+            if (int rc = do_match(h, planes0[f], planes1[f], n, rows, cols, pitch_bytes, depth, cfg, 0, rows, disparity[f],
+                                  disparity_pitch_bytes, corrmap ? corrmap[f] : nullptr, corrmap_pitch_bytes, static_cast<cudaStream_t>(stream)))
+                return rc;
+        return 0;
+    }
+    if (int rc = run_pipeline(h, units, sh, static_cast<cudaStream_t>(stream)))
+        return rc;
+    h->stage_count += count;
+    return 0;
+}
+
+int bicos_b200_set_overlap(bicos_b200_handle h, int enabled) {
+    if (!h)
+        return fail(BICOS_B200_ERR_INVALID, "null handle");
+    h->overlap = enabled != 0;
+    return 0;
 }
 
 // dense host planes that lie back to back in one allocation ([n][rows][cols], e.g. one numpy
@@ -838,9 +1046,14 @@ int bicos_b200_match_host_begin(bicos_b200_handle h, const void* const* host_pla
     int cut[MAX_BANDS + 1];
     int bands = 0;
     {
-        int inner = rows / 192;
+        static const int band_rows = [] { // BICOS_B200_HOST_BAND_ROWS: for sweeps of the host pipeline
+            const char* v = getenv("BICOS_B200_HOST_BAND_ROWS");
+            const int r = v ? atoi(v) : 0;
+            return r >= 16 ? r : 192;
+        }();
+        int inner = rows / band_rows;
         inner = inner < 1 ? 1 : inner > MAX_BANDS - 2 ? MAX_BANDS - 2 : inner;
-        const int edge = rows >= 4 * 192 ? 64 : 0; // only worth it when there are several bands anyway
+        const int edge = rows >= 4 * band_rows ? 64 : 0; // only worth it when there are several bands anyway
         cut[bands++] = 0;
         if (edge)
             cut[bands++] = edge;

@@ -537,6 +537,37 @@ def test_match_host_pipelined(handle, oracles):
     other.close()
 
 
+def test_match_batch_equals_single_matches(handle, oracles):
+    """bicos_b200_match_batch (frames through two internal streams, frame f + 1's search beside frame f's refine, key
+    buffers alternating) gives every frame exactly what bicos_b200_match gives it, and what the oracle gives."""
+    import torch
+
+    kw = dict(nxcorr_threshold=0.96, min_variance=2.0, subpixel_step=0.1, consistency=True, max_lr_diff=1)
+    cfg = Config(**kw)
+    host = [synth.make_stacks(33, 1024, 512, np.uint8, seed=31, frame=f, row0=200, rows=160)[:2] for f in range(5)]
+    frames = [(_cuda(l), _cuda(r)) for l, r in host]
+    single = [handle.match(l, r, cfg) for l, r in frames]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        outs = handle.match_batch(frames, cfg)
+        assert lb.last_search_kernel() == "mma2<K=4,nodupes=0,ct=1,dirs=2>" or torch.cuda.get_device_properties(0).multi_processor_count != 148
+        # stream-ordered: consuming the results on the current stream needs no synchronisation of our own
+        for (d, c), (sd, sc) in zip(outs, single):
+            assert torch.equal(torch.nan_to_num(d, nan=-9.0), torch.nan_to_num(sd, nan=-9.0))
+            assert torch.equal(torch.nan_to_num(c, nan=-9.0), torch.nan_to_num(sc, nan=-9.0))
+    for f in (0, 4):
+        want_d, want_c = oracles.port.match(host[f][0], host[f][1], **kw)
+        assert _same(outs[f][0].cpu().numpy(), want_d) and _same(outs[f][1].cpu().numpy(), want_c)
+    # reused outputs, no threshold (int16, no corrmap), odd batch of one
+    cfg_i = Config(nxcorr_threshold=None)
+    one = handle.match_batch(frames[:1], cfg_i)
+    assert one[0][1] is None and _same(one[0][0].cpu().numpy(), oracles.port.match(host[0][0], host[0][1], nxcorr_threshold=None)[0])
+    outs2 = handle.match_batch(frames, cfg, outs=outs)
+    assert outs2[0][0] is outs[0][0]
+    with pytest.raises(lb.BicosError, match="agree"):
+        handle.match_batch([frames[0], (frames[1][0][:, :100].contiguous(), frames[1][1][:, :100].contiguous())], cfg)
+
+
 def test_out_buffers_are_validated(handle):
     """Caller-supplied output buffers of the wrong type, shape, device or layout are refused before any kernel
     or copy can write past them (the C ABI takes plain pointers and trusts them)."""
@@ -686,6 +717,14 @@ def test_full_size_properties(handle):
     disp2, corr2 = handle.match(l, r, cfg)
     assert torch.equal(torch.nan_to_num(disp, nan=-9.0), torch.nan_to_num(disp2, nan=-9.0))
     assert torch.equal(torch.nan_to_num(corr, nan=-9.0), torch.nan_to_num(corr2, nan=-9.0))
+    # a match of this size runs as three row bands through the two-stream pipeline: same bits as one unit on one stream
+    handle.set_overlap(False)
+    try:
+        disp3, corr3 = handle.match(l, r, cfg)
+    finally:
+        handle.set_overlap(True)
+    assert torch.equal(torch.nan_to_num(disp, nan=-9.0), torch.nan_to_num(disp3, nan=-9.0))
+    assert torch.equal(torch.nan_to_num(corr, nan=-9.0), torch.nan_to_num(corr3, nan=-9.0))
     # row independence: matching a row band alone gives exactly the rows of the full match
     sub = handle.match(l[:, 700:764].contiguous(), r[:, 700:764].contiguous(), cfg)
     assert torch.equal(torch.nan_to_num(sub[0], nan=-9.0), torch.nan_to_num(disp[700:764], nan=-9.0))

@@ -126,3 +126,19 @@ def test_row_sharded_match_on_two_gpus(tmp_path, oracles):
     for kind in ("peer", "gather"):
         assert np.array_equal(np.load(tmp_path / f"{kind}_disp.npy"), want_d, equal_nan=True), kind
         assert np.array_equal(np.load(tmp_path / f"{kind}_corr.npy"), want_c, equal_nan=True), kind
+
+
+def test_topology_pick_is_a_pure_function_of_the_matrix():
+    """libbicos_b200.topology.choose: ranks spread over the PCIe tree NVML reports; every rank computes the same list."""
+    from libbicos_b200 import topology
+
+    def level(i, j):  # an HGX-like tree: GPU pairs on a switch, two switches per host bridge, two bridges
+        return 0 if i == j else 10 if i // 2 == j // 2 else 30 if i // 4 == j // 4 else 50
+
+    tree = [[level(i, j) for j in range(8)] for i in range(8)]
+    assert topology.choose(2, tree)[0] == [0, 4]
+    assert topology.choose(4, tree)[0] == [0, 2, 4, 6]
+    flat = [[0 if i == j else 50 for j in range(8)] for i in range(8)]
+    assert topology.choose(4, flat)[0] == [0, 2, 4, 6] and "flat" in topology.choose(4, flat)[1]
+    assert topology.spread(2, 8) == [0, 4] and topology.spread(8, 8) == list(range(8))
+    assert isinstance(topology.describe(), dict)  # without NVML: {"unavailable": ...}
