@@ -388,6 +388,26 @@ def main():
     e2e_value = world * FRAMES * px / (e2e_ms * 1e-3) / 1e6
     same = bool(np.array_equal(host_out[0][0], outs[0][0].cpu().numpy(), equal_nan=True))
 
+    # the ceiling of that path: what plain pinned host-to-device copies reach on the same GPUs at the same time
+    # (256 MB each, all ranks concurrently; one GPU alone gets about 55 GB/s, GPUs behind one host bridge share it)
+    link_host = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    link_dev = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        link_dev.copy_(link_host, non_blocking=True)
+    barrier()
+    ev0.record()
+    for _ in range(8):
+        link_dev.copy_(link_host, non_blocking=True)
+    ev1.record()
+    barrier()
+    link_gbs = 8 * (256 << 20) / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+    if world > 1:
+        t = torch.tensor([link_gbs], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        link_gbs = float(t.item())
+    del link_host, link_dev
+    e2e_h2d_gbs = world * FRAMES * 2 * N_IMAGES * px / (e2e_ms * 1e-3) / 1e9
+
     # ---- N > 1: ONE match of the same workload row-sharded over the N GPUs (strong scaling; BASELINE.json
     #      configs[2] / [3] ask for this mode). Rank g holds rows [g H / N, (g + 1) H / N) of frame 0 and runs the
     #      whole path on them; the refine kernels store their rows into rank 0's images over NVLink peer memory
@@ -573,6 +593,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": FRAMES * 2 * N_IMAGES * px,
                 "d2h_bytes_per_step": FRAMES * px * 8, "ms_per_step": e2e_ms, "matches_device_path": same, "host_affinity": affinity,
                 "devices": devices, "device_policy": device_policy,
+                "h2d_gbs": e2e_h2d_gbs, "link_gbs": link_gbs, "link_frac": e2e_h2d_gbs / link_gbs,
+                "link_note": "link_gbs = plain 256 MB pinned host-to-device copies on the same GPUs, all ranks at once; the "
+                             "device-to-host results (12 % of the bytes) travel the other direction of the link at the same time",
                 "api": f"bicos_b200_match_host_begin/_end, {inflight} frames in flight (pinned host stacks -> host disparity + corrmap)"},
         "gpu_launches": launches,
         "stage_ms_per_match": {"transform_x2": t_tr * 1e3, "search": t_se * 1e3, "refine": t_re * 1e3,

@@ -2,6 +2,7 @@
 
 #include <zlib.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -203,6 +204,262 @@ GrayImage read_pgm(const std::vector<uint8_t>& file, const std::string& path) {
     return img;
 }
 
+// ---- TIFF input: what camera tools write (the reference reads it through cv::imread, src/fileutils.cpp:72-75,116).
+// Baseline TIFF 6.0, strips: 8 / 16-bit grey (either photometric) and 8 / 16-bit RGB[A] (-> luma, like the PNG
+// reader), little or big endian, uncompressed, LZW (with or without the horizontal predictor), Deflate and
+// PackBits. Tiles, palettes, sub-byte depths, JPEG-in-TIFF and planar RGB are refused with a message.
+struct TiffReader {
+    const std::vector<uint8_t>& f;
+    const std::string& path;
+    bool big = false;
+    [[noreturn]] void fail(const char* what) const {
+        throw std::runtime_error(path + ": " + what);
+    }
+    uint16_t u16(size_t at) const {
+        if (at + 2 > f.size())
+            fail("truncated TIFF");
+        return big ? (uint16_t)(f[at] << 8 | f[at + 1]) : (uint16_t)(f[at] | f[at + 1] << 8);
+    }
+    uint32_t u32(size_t at) const {
+        if (at + 4 > f.size())
+            fail("truncated TIFF");
+        return big ? ((uint32_t)f[at] << 24 | (uint32_t)f[at + 1] << 16 | (uint32_t)f[at + 2] << 8 | f[at + 3])
+                   : ((uint32_t)f[at + 3] << 24 | (uint32_t)f[at + 2] << 16 | (uint32_t)f[at + 1] << 8 | f[at]);
+    }
+    // values of an IFD entry (types BYTE, SHORT, LONG), wherever they are stored
+    std::vector<uint32_t> values(size_t entry) const {
+        const uint16_t type = u16(entry + 2);
+        const uint32_t count = u32(entry + 4);
+        const size_t size = type == 1 ? 1 : type == 3 ? 2 : type == 4 ? 4 : 0;
+        if (size == 0)
+            fail("TIFF tag of an unsupported type");
+        if (count > (1u << 24))
+            fail("TIFF tag with an absurd count");
+        size_t at = entry + 8;
+        if (size * count > 4)
+            at = u32(entry + 8);
+        std::vector<uint32_t> v(count);
+        for (uint32_t i = 0; i < count; ++i)
+            v[i] = size == 1 ? (at + i < f.size() ? f[at + i] : (fail("truncated TIFF"), 0u)) : size == 2 ? u16(at + 2 * (size_t)i) : u32(at + 4 * (size_t)i);
+        return v;
+    }
+};
+
+// TIFF flavour of LZW: codes MSB first, 9 to 12 bits, width grows one code early, 256 = clear, 257 = end
+void tiff_lzw(const uint8_t* src, size_t n, std::vector<uint8_t>& out, size_t expect) {
+    struct Entry {
+        uint16_t prefix;
+        uint8_t last, first;
+        uint16_t length;
+    };
+    std::vector<Entry> table(4096);
+    for (int i = 0; i < 256; ++i)
+        table[i] = { 0xFFFF, (uint8_t)i, (uint8_t)i, 1 };
+    int next = 258, width = 9, prev = -1;
+    uint32_t acc = 0;
+    int bits = 0;
+    size_t pos = 0;
+    const size_t start = out.size();
+    while (out.size() - start < expect) {
+        while (bits < width && pos < n) {
+            acc = (acc << 8) | src[pos++];
+            bits += 8;
+        }
+        if (bits < width)
+            break;
+        const int code = (int)((acc >> (bits - width)) & ((1u << width) - 1));
+        bits -= width;
+        if (code == 257)
+            break;
+        if (code == 256) {
+            next = 258;
+            width = 9;
+            prev = -1;
+            continue;
+        }
+        Entry e;
+        if (code < next && (code < 256 || code >= 258)) {
+            e = table[code];
+        } else if (code == next && prev >= 0) { // the string being defined: previous string + its own first byte
+            e = { (uint16_t)prev, table[prev].first, table[prev].first, (uint16_t)(table[prev].length + 1) };
+        } else {
+            throw std::runtime_error("corrupt LZW data in TIFF");
+        }
+        const size_t at = out.size();
+        out.resize(at + e.length);
+        {
+            size_t w = at + e.length;
+            out[--w] = e.last;
+            int c = e.prefix;
+            while (c != 0xFFFF && w > at) {
+                out[--w] = table[c].last;
+                c = table[c].prefix;
+            }
+        }
+        if (prev >= 0 && next < 4096) {
+            table[next] = { (uint16_t)prev, out[at], table[prev].first, (uint16_t)(table[prev].length + 1) };
+            ++next;
+            if (next + 1 >= (1 << width) && width < 12)
+                ++width;
+        }
+        prev = code;
+    }
+}
+
+void tiff_packbits(const uint8_t* src, size_t n, std::vector<uint8_t>& out, size_t expect) {
+    const size_t start = out.size();
+    size_t pos = 0;
+    while (pos < n && out.size() - start < expect) {
+        const int8_t c = (int8_t)src[pos++];
+        if (c >= 0) {
+            const size_t len = (size_t)c + 1;
+            if (pos + len > n)
+                throw std::runtime_error("corrupt PackBits data in TIFF");
+            out.insert(out.end(), src + pos, src + pos + len);
+            pos += len;
+        } else if (c != -128) {
+            if (pos >= n)
+                throw std::runtime_error("corrupt PackBits data in TIFF");
+            out.insert(out.end(), (size_t)(1 - c), src[pos++]);
+        }
+    }
+}
+
+GrayImage read_tiff(const std::vector<uint8_t>& file, const std::string& path, bool& was_colour) {
+    TiffReader t { file, path };
+    t.big = file[0] == 'M';
+    if (t.u16(2) != 42)
+        t.fail("not a TIFF file (BigTIFF is not supported)");
+    const size_t ifd = t.u32(4);
+    const int entries = t.u16(ifd);
+    uint32_t width = 0, height = 0, bits = 1, compression = 1, photometric = 1, spp = 1, rows_per_strip = 0xFFFFFFFFu;
+    uint32_t planar = 1, predictor = 1, sample_format = 1;
+    std::vector<uint32_t> offsets, counts;
+    for (int e = 0; e < entries; ++e) {
+        const size_t at = ifd + 2 + 12 * (size_t)e;
+        const uint16_t tag = t.u16(at);
+        auto first = [&] {
+            const std::vector<uint32_t> v = t.values(at);
+            if (v.empty())
+                t.fail("empty TIFF tag");
+            return v;
+        };
+        switch (tag) {
+            case 256: width = first()[0]; break;
+            case 257: height = first()[0]; break;
+            case 258: {
+                const std::vector<uint32_t> v = first();
+                bits = v[0];
+                for (uint32_t b: v)
+                    if (b != bits)
+                        t.fail("TIFF samples of different depths");
+                break;
+            }
+            case 259: compression = first()[0]; break;
+            case 262: photometric = first()[0]; break;
+            case 273: offsets = first(); break;
+            case 277: spp = first()[0]; break;
+            case 278: rows_per_strip = first()[0]; break;
+            case 279: counts = first(); break;
+            case 284: planar = first()[0]; break;
+            case 317: predictor = first()[0]; break;
+            case 339: sample_format = first()[0]; break;
+            case 322: case 323: case 324: case 325: t.fail("tiled TIFF is not supported");
+            default: break;
+        }
+    }
+    if (width == 0 || height == 0 || width > 32767u || height > 65535u)
+        t.fail("TIFF without a size, or larger than 32767 x 65535");
+    if (bits != 8 && bits != 16)
+        t.fail("only 8- and 16-bit TIFF samples are supported");
+    if (sample_format != 1)
+        t.fail("only unsigned integer TIFF samples are supported");
+    if (photometric > 2 || (photometric == 2 && spp < 3) || (photometric < 2 && spp > 2) || spp > 4)
+        t.fail("unsupported TIFF photometric interpretation");
+    if (planar != 1 && spp > 1)
+        t.fail("planar TIFF is not supported");
+    if (compression != 1 && compression != 5 && compression != 8 && compression != 32946 && compression != 32773)
+        t.fail("unsupported TIFF compression (none, LZW, Deflate and PackBits are read)");
+    if (predictor != 1 && predictor != 2)
+        t.fail("unsupported TIFF predictor");
+    if (offsets.empty() || offsets.size() != counts.size())
+        t.fail("TIFF without strips");
+    if (rows_per_strip == 0)
+        t.fail("TIFF with zero rows per strip");
+    rows_per_strip = std::min(rows_per_strip, height);
+    if ((size_t)(height + rows_per_strip - 1) / rows_per_strip != offsets.size())
+        t.fail("TIFF strip count does not match its height");
+
+    const size_t bps = bits / 8;
+    const size_t row_bytes = (size_t)width * spp * bps;
+    std::vector<uint8_t> raw;
+    raw.reserve(row_bytes * height);
+    for (size_t sidx = 0; sidx < offsets.size(); ++sidx) {
+        const size_t rows_here = std::min<size_t>(rows_per_strip, height - sidx * rows_per_strip);
+        const size_t expect = rows_here * row_bytes;
+        if ((size_t)offsets[sidx] + counts[sidx] > file.size())
+            t.fail("TIFF strip beyond the end of the file");
+        const uint8_t* src = &file[offsets[sidx]];
+        const size_t before = raw.size();
+        if (compression == 1) {
+            if (counts[sidx] < expect)
+                t.fail("short TIFF strip");
+            raw.insert(raw.end(), src, src + expect);
+        } else if (compression == 5) {
+            tiff_lzw(src, counts[sidx], raw, expect);
+        } else if (compression == 32773) {
+            tiff_packbits(src, counts[sidx], raw, expect);
+        } else {
+            raw.resize(before + expect);
+            uLongf out_len = expect;
+            if (uncompress(&raw[before], &out_len, src, counts[sidx]) != Z_OK || out_len != expect)
+                t.fail("TIFF strip does not inflate");
+        }
+        if (raw.size() - before < expect)
+            t.fail("short TIFF strip");
+        raw.resize(before + expect);
+        if (predictor == 2) // horizontal differencing, per sample, in the file's byte order
+            for (size_t y = 0; y < rows_here; ++y) {
+                uint8_t* line = &raw[before + y * row_bytes];
+                if (bps == 1) {
+                    for (size_t i = spp; i < (size_t)width * spp; ++i)
+                        line[i] = (uint8_t)(line[i] + line[i - spp]);
+                } else {
+                    auto get = [&](size_t i) { return t.big ? (uint16_t)(line[2 * i] << 8 | line[2 * i + 1]) : (uint16_t)(line[2 * i] | line[2 * i + 1] << 8); };
+                    for (size_t i = spp; i < (size_t)width * spp; ++i) {
+                        const uint16_t v = (uint16_t)(get(i) + get(i - spp));
+                        line[2 * i + (t.big ? 0 : 1)] = (uint8_t)(v >> 8);
+                        line[2 * i + (t.big ? 1 : 0)] = (uint8_t)v;
+                    }
+                }
+            }
+    }
+
+    GrayImage img;
+    img.rows = (int)height;
+    img.cols = (int)width;
+    img.bits = (int)bits;
+    img.data.resize((size_t)width * height * bps);
+    was_colour = photometric == 2;
+    const uint32_t maxv = bits == 16 ? 65535u : 255u;
+    for (size_t px = 0; px < (size_t)width * height; ++px) {
+        auto sample = [&](size_t c) -> uint32_t {
+            const uint8_t* p = &raw[(px * spp + c) * bps];
+            return bps == 1 ? p[0] : t.big ? (uint32_t)(p[0] << 8 | p[1]) : (uint32_t)(p[0] | p[1] << 8);
+        };
+        uint32_t v = photometric == 2 ? luma(sample(0), sample(1), sample(2)) : sample(0);
+        if (photometric == 0 && bps == 1)
+            v = maxv - v; // WhiteIsZero: inverted for 8-bit samples only -- OpenCV's reader, i.e. what the reference sees, returns 16-bit samples as stored
+        if (bps == 1) {
+            img.data[px] = (uint8_t)v;
+        } else {
+            const uint16_t w = (uint16_t)v;
+            std::memcpy(&img.data[2 * px], &w, 2);
+        }
+    }
+    return img;
+}
+
 void put_be32(std::vector<uint8_t>& v, uint32_t x) {
     v.push_back(x >> 24);
     v.push_back(x >> 16);
@@ -225,6 +482,8 @@ GrayImage read_image(const std::string& path, bool& was_colour) {
     const std::vector<uint8_t> file = slurp(path);
     if (file.size() >= 2 && file[0] == 'P' && file[1] == '5')
         return read_pgm(file, path);
+    if (file.size() >= 8 && ((file[0] == 'I' && file[1] == 'I') || (file[0] == 'M' && file[1] == 'M')))
+        return read_tiff(file, path, was_colour);
     return read_png(file, path, was_colour);
 }
 

@@ -3,8 +3,9 @@
 //   reference src/fileutils.cpp:30-154 (save_image, read_sequence, sort_sequence_to_stack)
 //   reference include/fileutils.hpp:43-89 (save_pointcloud)
 //   reference src/cli.cpp:228-250 (Q matrix, reprojection)
-// Readers: PNG (8/16-bit gray, gray+alpha, RGB, RGBA, palette; non-interlaced) and binary PGM
-// (P5, 8/16 bit). Writers: 8-bit RGB PNG, single-strip uncompressed TIFF (int16 / float32 /
+// Readers: PNG (8/16-bit gray, gray+alpha, RGB, RGBA, palette; non-interlaced), binary PGM
+// (P5, 8/16 bit) and strip TIFF (8/16-bit gray or RGB[A]; uncompressed, LZW, Deflate, PackBits; both
+// byte orders) -- the formats multi-shot camera rigs dump. Writers: 8-bit RGB PNG, single-strip uncompressed TIFF (int16 / float32 /
 // float64), ASCII .xyz. zlib is the only library used.
 #pragma once
 

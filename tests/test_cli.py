@@ -58,6 +58,68 @@ def test_image_reader_matches_opencv_grey(tmp_path, dtype, ext):
     assert not colour and got.dtype == dtype and np.array_equal(got, img)
 
 
+TIFF_FLAGS = {"none": 1, "lzw": 5, "deflate": 32946, "packbits": 32773}
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+@pytest.mark.parametrize("compression", sorted(TIFF_FLAGS))
+def test_tiff_reader_matches_opencv(tmp_path, dtype, compression):
+    """TIFF input (16-bit camera dumps): every compression OpenCV's writer offers, one strip and several, smooth
+    content (long LZW strings, the horizontal predictor OpenCV switches on for LZW / Deflate) and noise."""
+    rng = np.random.default_rng(7)
+    hi = np.iinfo(dtype).max
+    smooth = (np.add.outer(np.arange(301), np.arange(517)) * (hi // 900)).astype(dtype)
+    noise = rng.integers(0, hi + 1, size=(64, 129)).astype(dtype)
+    flat = np.full((70, 333), hi // 3, dtype)
+    for k, img in enumerate((smooth, noise, flat)):
+        for rps in (0, 7):
+            path = str(tmp_path / f"t{k}_{rps}.tiff")
+            params = [cv2.IMWRITE_TIFF_COMPRESSION, TIFF_FLAGS[compression]]
+            if rps:
+                params += [cv2.IMWRITE_TIFF_ROWSPERSTRIP, rps]
+            assert cv2.imwrite(path, img, params)
+            got, colour = _read_with_tool(path, str(tmp_path))
+            assert not colour and got.dtype == dtype and np.array_equal(got, img), (k, rps)
+            assert np.array_equal(cv2.imread(path, cv2.IMREAD_UNCHANGED), img)
+
+
+def test_tiff_reader_colour_big_endian_and_errors(tmp_path):
+    rng = np.random.default_rng(8)
+    bgr = rng.integers(0, 256, size=(21, 40, 3)).astype(np.uint8)
+    path = str(tmp_path / "rgb.tif")
+    assert cv2.imwrite(path, bgr, [cv2.IMWRITE_TIFF_COMPRESSION, 5])
+    got, colour = _read_with_tool(path, str(tmp_path))
+    want = cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
+    assert colour and np.abs(got.astype(int) - want.astype(int)).max() <= 1
+    # hand-made big-endian ("MM"), WhiteIsZero, uncompressed files: whatever cv::imread hands the reference is the truth
+    # (it inverts 8-bit WhiteIsZero samples and returns 16-bit ones as stored)
+    for dtype, bits in ((np.uint8, 8), (np.uint16, 16)):
+        img = rng.integers(0, np.iinfo(dtype).max + 1, size=(5, 9)).astype(dtype)
+        data = img.astype(">u2").tobytes() if bits == 16 else img.tobytes()
+        tags = [(256, 3, 1, 9), (257, 3, 1, 5), (258, 3, 1, bits), (259, 3, 1, 1), (262, 3, 1, 0), (273, 4, 1, 8),
+                (277, 3, 1, 1), (278, 3, 1, 5), (279, 4, 1, len(data))]
+        ifd = len(tags).to_bytes(2, "big")
+        for tag, typ, cnt, val in tags:
+            ifd += tag.to_bytes(2, "big") + typ.to_bytes(2, "big") + cnt.to_bytes(4, "big")
+            ifd += (val.to_bytes(2, "big") + b"\0\0") if typ == 3 else val.to_bytes(4, "big")
+        ifd += (0).to_bytes(4, "big")
+        blob = b"MM" + (42).to_bytes(2, "big") + (8 + len(data)).to_bytes(4, "big") + data + ifd
+        mm = tmp_path / f"mm{bits}.tif"
+        mm.write_bytes(blob)
+        got, colour = _read_with_tool(str(mm), str(tmp_path))
+        want = cv2.imread(str(mm), cv2.IMREAD_GRAYSCALE | cv2.IMREAD_ANYDEPTH)  # the reference's flags (fileutils.cpp:72-75)
+        assert not colour and got.dtype == dtype and np.array_equal(got, want)
+        assert np.array_equal(want, 255 - img if bits == 8 else img)
+    # refused with a message, never a crash: truncated file, float samples
+    (tmp_path / "cut.tif").write_bytes(blob[: len(blob) // 2])
+    res = subprocess.run([IOCHK, "read", str(tmp_path / "cut.tif"), str(tmp_path / "x.raw")], capture_output=True, text=True)
+    assert res.returncode == 1 and "cut.tif" in res.stderr
+    f32 = str(tmp_path / "f.tiff")
+    assert cv2.imwrite(f32, rng.random((4, 4)).astype(np.float32))
+    res = subprocess.run([IOCHK, "read", f32, str(tmp_path / "x.raw")], capture_output=True, text=True)
+    assert res.returncode == 1 and "TIFF" in res.stderr
+
+
 def test_image_reader_colour_and_alpha(tmp_path):
     rng = np.random.default_rng(6)
     bgr = rng.integers(0, 256, size=(21, 40, 3)).astype(np.uint8)
@@ -132,6 +194,8 @@ def _write_stacks(folder, left, right, paired, ext):
      dict(nxcorr_threshold=0.9, subpixel_step=0.25, consistency=True, max_lr_diff=1)),
     (np.uint8, "pgm", False, ["-t", "0", "-n", "12", "-v", "0"],
      dict(nxcorr_threshold=None, mode_full=True)),
+    (np.uint16, "tiff", True, ["-t", "0.9", "-v", "2.0", "--limited", "-s", "0.5"],
+     dict(nxcorr_threshold=0.9, min_variance=2.0, subpixel_step=0.5)),
 ])
 def test_cli_folder_to_disparity(tmp_path, oracles, dtype, ext, paired, args, kw):
     n = 20

@@ -33,4 +33,4 @@ for f in sorted(glob.glob("$O/r02_scale_n*bench.json")):
         print(f, "unreadable", e)
 PY
 cat $O/r02_scale_n${N}_rowshard.jsonl
-[ -n "$FULL" ] && cat $O/r02_scale_n${N}_batch.jsonl $O/r02_h2d_topology_n${N}.json
+if [ -n "$FULL" ]; then cat $O/r02_scale_n${N}_batch.jsonl $O/r02_h2d_topology_n${N}.json; fi
