@@ -889,14 +889,16 @@ int bicos_b200_refine(bicos_b200_handle h, const void* const* planes0, const voi
                      static_cast<cudaStream_t>(stream));
 }
 
-// A single match of a large image with the subpixel refine (the FP32-heavy one): as three row bands through the
-// two-stream pipeline, band b + 1's search beside band b's refine. Rows are independent, so the result is the same;
-// measured on the metric configuration: 1.91 against 2.01 ms (2 bands 1.93, 4 bands 1.91; tools/overlap_probe.py).
-// Small images, integer refinement and the popcount engine (which leaves no issue slots free) run as one unit.
+// A single match of a large image with the subpixel refine (the FP32-heavy one): as row bands through the two-stream
+// pipeline, band b + 1's search beside band b's refine. Rows are independent, so the result is the same. Measured with
+// tools/overlap_probe.py --frames 1: 1536 rows 2.01 ms as one unit, 1.93 / 1.91 / 1.91 ms as 2 / 3 / 4 bands; 768 rows
+// (a shard of a two-GPU match) 1.025 -> 0.991 / 0.989 ms as 2 / 3 bands; 384 rows: no gain. Small images, integer
+// refinement and the popcount engine (which leaves no issue slots free) run as one unit.
 static int match_banded_or_whole(bicos_b200_handle h, const void* const* planes0, const void* const* planes1, int n, int rows,
                                  int cols, size_t pitch_bytes, int depth, const bicos_b200_config* cfg, void* disparity,
                                  size_t disparity_pitch, void* corrmap, size_t corrmap_pitch, cudaStream_t stream) {
-    constexpr int BANDS = 3, MIN_BAND_ROWS = 384;
+    const int BANDS = rows >= 1152 ? 3 : 2;
+    constexpr int MIN_BAND_ROWS = 320;
     MatchShape sh {};
     if (int rc = validate_match(planes0, planes1, n, rows, cols, pitch_bytes, depth, cfg, disparity, sh))
         return rc;
@@ -906,7 +908,7 @@ static int match_banded_or_whole(bicos_b200_handle h, const void* const* planes0
                         corrmap_pitch, stream);
     sh.disparity_pitch = disparity_pitch;
     sh.corrmap_pitch = corrmap_pitch;
-    std::vector<Unit> units(BANDS);
+    std::vector<Unit> units((size_t)BANDS);
     for (int b = 0; b < BANDS; ++b)
         if (int rc = make_unit(units[(size_t)b], planes0, planes1, sh, (int)((long long)rows * b / BANDS),
                                (int)((long long)rows * (b + 1) / BANDS), disparity, corrmap))
