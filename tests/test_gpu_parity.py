@@ -568,6 +568,86 @@ def test_match_batch_equals_single_matches(handle, oracles):
         handle.match_batch([frames[0], (frames[1][0][:, :100].contiguous(), frames[1][1][:, :100].contiguous())], cfg)
 
 
+@pytest.mark.parametrize("n,dtype,full,rows,cols,kw", [
+    (33, np.uint8, False, 7, 300, dict(nxcorr_threshold=0.9, subpixel_step=0.25, consistency=True, max_lr_diff=1, no_dupes=True)),
+    (33, np.uint8, False, 150, 513, dict(nxcorr_threshold=0.9, subpixel_step=0.5, consistency=True)),  # search_mma2, ragged tiles
+    (64, np.uint8, False, 150, 300, dict(nxcorr_threshold=0.9)),  # search_mma2, 256 bits
+    (16, np.uint16, True, 5, 131, dict(nxcorr_threshold=0.9, double=True, min_variance=1.0)),
+    (9, np.uint8, False, 3, 1, dict(nxcorr_threshold=None)),  # 32-bit descriptors: popcount engine
+    (20, np.uint16, True, 4, 129, dict(nxcorr_threshold=0.8, wide_descriptors=True, consistency=True)),  # 12 words, variant 1
+])
+def test_kernels_write_only_their_buffers(handle, n, dtype, full, rows, cols, kw):
+    """Our own memcheck for stores (compute-sanitizer is closed on this GPU pool): descriptors, the four key arrays,
+    disparity and corrmap sit inside one allocation each, surrounded by guard words; after the three stages and after
+    the whole match every guard word is intact and the interior is completely written. Stage entry points through the
+    C ABI with interior pointers."""
+    import ctypes
+
+    import torch
+
+    from libbicos_b200 import capi
+
+    L = lb.lib()
+    cfg = Config(mode_full=full, **kw)
+    ccfg = cfg.to_c()
+    left, right, _ = synth.make_stacks(n, 64, max(cols, 16), dtype, seed=n + cols, rows=rows)
+    l, r = _cuda(np.ascontiguousarray(left[:, :, :cols])), _cuda(np.ascontiguousarray(right[:, :, :cols]))
+    p0, _, _, _, pitch, depth = handle._stack_info(l)
+    p1 = handle._stack_info(r)[0]
+    k = lb.descriptor_words(n, full, cfg.wide_descriptors)
+    pw = (cols * k + 3) // 4 * 4
+    GUARD, MARK = 1024, 0x5A5A5A5A - (1 << 32)  # int32 words
+
+    def guarded(words):
+        buf = torch.full((GUARD + words + GUARD,), MARK, dtype=torch.int32, device="cuda")
+        return buf, buf.data_ptr() + 4 * GUARD
+
+    def intact(buf, words, what, filled=True):
+        assert bool((buf[:GUARD] == MARK).all()) and bool((buf[GUARD + words:] == MARK).all()), f"{what}: guard words overwritten"
+        if filled:
+            assert int((buf[GUARD : GUARD + words] == MARK).sum()) == 0, f"{what}: interior not completely written"
+
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    mode = int(full) | (capi.MODE_WIDE if cfg.wide_descriptors else 0)
+    px = rows * cols
+    for engine in ("auto", "popc"):
+        lb.set_search_engine(engine)
+        try:
+            d = [guarded(rows * pw) for _ in range(2)]
+            for planes, (buf, ptr) in zip((p0, p1), d):
+                capi._check(L.bicos_b200_transform(handle._h, planes, n, rows, cols, pitch, depth, mode, ptr, pw, st))
+            keys = [guarded(px) for _ in range(4)]
+            flags = cfg.flags
+            ptrs = [keys[0][1], keys[1][1] if flags & 1 else None, keys[2][1] if flags & 2 else None, keys[3][1] if flags == 3 else None]
+            capi._check(L.bicos_b200_search(handle._h, d[0][1], d[1][1], k, rows, cols, pw, flags | capi.FLAG_TOP_BIT_FREE, *ptrs, st))
+            disp_words = px if cfg.nxcorr_threshold is not None else (px + 1) // 2
+            corr_words = px * (2 if cfg.double else 1)
+            raw, disp, corr = guarded((px + 1) // 2), guarded(disp_words), guarded(corr_words)
+            disp_pitch = cols * (4 if cfg.nxcorr_threshold is not None else 2)
+            capi._check(L.bicos_b200_refine(handle._h, p0, p1, n, rows, cols, pitch, depth, ctypes.byref(ccfg), *ptrs, raw[1],
+                                            disp[1], disp_pitch, corr[1] if cfg.nxcorr_threshold is not None else None,
+                                            cols * (8 if cfg.double else 4), st))
+            torch.cuda.synchronize()
+            odd = px % 2 == 1  # the last int16 of an odd image shares its word with the guard pattern
+            for (buf, _), what in zip(d, ("desc0", "desc1")):
+                intact(buf, rows * pw, what, filled=pw == cols * k)
+            for (buf, _), ptr, what in zip(keys, ptrs, ("fwd_first", "fwd_last", "rev_first", "rev_last")):
+                intact(buf, px, what, filled=ptr is not None)
+            intact(raw[0], (px + 1) // 2, "raw disparity", filled=not odd)
+            intact(disp[0], disp_words, "disparity", filled=cfg.nxcorr_threshold is not None or not odd)
+            intact(corr[0], corr_words, "corrmap", filled=cfg.nxcorr_threshold is not None)
+            # the whole path into fresh guarded outputs
+            disp2, corr2 = guarded(disp_words), guarded(corr_words)
+            capi._check(L.bicos_b200_match(handle._h, p0, p1, n, rows, cols, pitch, depth, ctypes.byref(ccfg), disp2[1], disp_pitch,
+                                           corr2[1] if cfg.nxcorr_threshold is not None else None, cols * (8 if cfg.double else 4), st))
+            torch.cuda.synchronize()
+            intact(disp2[0], disp_words, "match disparity", filled=cfg.nxcorr_threshold is not None or not odd)
+            intact(corr2[0], corr_words, "match corrmap", filled=cfg.nxcorr_threshold is not None)
+            assert torch.equal(disp2[0], disp[0]) and torch.equal(corr2[0], corr[0])
+        finally:
+            lb.set_search_engine("auto")
+
+
 def test_out_buffers_are_validated(handle):
     """Caller-supplied output buffers of the wrong type, shape, device or layout are refused before any kernel
     or copy can write past them (the C ABI takes plain pointers and trusts them)."""
