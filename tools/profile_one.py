@@ -19,6 +19,7 @@ if variant == "c4":  # 256-bit descriptors (n = 64), a row band of the 4096-colu
 else:
     l, r, _ = synth.make_stacks(33, 1536, 2048, np.uint8, xp=torch, device="cuda")
 h = lb.Handle(0)
+h.set_overlap(False)  # whole-frame kernels one after the other: what a per-kernel profile wants (ncu serialises anyway)
 cfg = lb.Config(**kw)
 out = h.match(l, r, cfg)
 torch.cuda.synchronize()
