@@ -596,7 +596,7 @@ def test_kernels_write_only_their_buffers(handle, n, dtype, full, rows, cols, kw
     p1 = handle._stack_info(r)[0]
     k = lb.descriptor_words(n, full, cfg.wide_descriptors)
     pw = (cols * k + 3) // 4 * 4
-    GUARD, MARK = 1024, 0x5A5A5A5A - (1 << 32)  # int32 words
+    GUARD, MARK = 1024, 0x5A5A5A5A  # int32 words
 
     def guarded(words):
         buf = torch.full((GUARD + words + GUARD,), MARK, dtype=torch.int32, device="cuda")
