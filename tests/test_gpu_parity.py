@@ -564,6 +564,15 @@ def test_match_batch_equals_single_matches(handle, oracles):
     assert one[0][1] is None and _same(one[0][0].cpu().numpy(), oracles.port.match(host[0][0], host[0][1], nxcorr_threshold=None)[0])
     outs2 = handle.match_batch(frames, cfg, outs=outs)
     assert outs2[0][0] is outs[0][0]
+    # overlap switched off: the same frames one after the other on the caller's stream, same bits
+    handle.set_overlap(False)
+    try:
+        outs3 = handle.match_batch(frames, cfg)
+    finally:
+        handle.set_overlap(True)
+    for (d, c), (sd, sc) in zip(outs3, single):
+        assert torch.equal(torch.nan_to_num(d, nan=-9.0), torch.nan_to_num(sd, nan=-9.0))
+        assert torch.equal(torch.nan_to_num(c, nan=-9.0), torch.nan_to_num(sc, nan=-9.0))
     with pytest.raises(lb.BicosError, match="agree"):
         handle.match_batch([frames[0], (frames[1][0][:, :100].contiguous(), frames[1][1][:, :100].contiguous())], cfg)
 
