@@ -1124,6 +1124,9 @@ int bicos_b200_match_host_begin(bicos_b200_handle h, const void* const* host_pla
     char* const out_disp = static_cast<char*>(stage_disp ? h->pin_disp.ptr : host_disparity);
     char* const out_corr = static_cast<char*>(stage_corr ? h->pin_corr.ptr : host_corrmap);
 
+    // PROBE (temporary, tools/e2e_probe.py): BICOS_B200_HOST_PROBE contains "nocompute" and / or "nod2h"
+    static const char* probe = getenv("BICOS_B200_HOST_PROBE");
+    const bool probe_nocompute = probe && strstr(probe, "nocompute"), probe_nod2h = probe && strstr(probe, "nod2h");
     // upload of band b is enqueued right before the match of band b, so the host never runs
     // far ahead of the device with copy submissions while kernels wait to be launched
     auto enqueue = [&]() -> int {
@@ -1154,6 +1157,7 @@ int bicos_b200_match_host_begin(bicos_b200_handle h, const void* const* host_pla
             }
             CU(cudaEventRecord(h->ev_in[b], h->s_in));
             CU(cudaStreamWaitEvent(h->s_compute, h->ev_in[b], 0));
+            if (!probe_nocompute)
             if (int rc = do_match(h, dev0.data(), dev1.data(), n, rows, cols, pitch, depth, cfg, rb, re,
                                   h->stage_disp.ptr, (size_t)cols * disp_eb, want_corr ? h->stage_corr.ptr : nullptr,
                                   (size_t)cols * corr_eb, h->s_compute))
@@ -1161,6 +1165,8 @@ int bicos_b200_match_host_begin(bicos_b200_handle h, const void* const* host_pla
             CU(cudaEventRecord(h->ev_done[b], h->s_compute));
             CU(cudaStreamWaitEvent(h->s_out, h->ev_done[b], 0));
             const size_t off = (size_t)rb * cols, cnt = (size_t)(re - rb) * cols;
+            if (probe_nod2h)
+                continue;
             CU(cudaMemcpyAsync(out_disp + off * disp_eb, static_cast<char*>(h->stage_disp.ptr) + off * disp_eb,
                                cnt * disp_eb, cudaMemcpyDeviceToHost, h->s_out));
             if (want_corr)
