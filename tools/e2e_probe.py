@@ -24,6 +24,39 @@ torch.cuda.set_device(local)
 if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+if os.environ.get("PROBE_PLAIN"):
+    # plain copies: 256 MB host-to-device on one stream, optionally 32 MB device-to-host on another at the same time
+    MB = 1 << 20
+    hsrc = torch.empty(256 * MB, dtype=torch.uint8).pin_memory()
+    ddst = torch.empty(256 * MB, dtype=torch.uint8, device="cuda")
+    dsrc = torch.empty(32 * MB, dtype=torch.uint8, device="cuda")
+    hdst = torch.empty(32 * MB, dtype=torch.uint8).pin_memory()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    both = os.environ["PROBE_PLAIN"] == "both"
+    for rep in range(2):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(s1):
+            a.record()
+            for _ in range(8):
+                ddst.copy_(hsrc, non_blocking=True)
+            b.record()
+        if both:
+            with torch.cuda.stream(s2):
+                for _ in range(8):
+                    hdst.copy_(dsrc, non_blocking=True)
+        torch.cuda.synchronize()
+    g = torch.tensor([8 * 256 * MB / (a.elapsed_time(b) * 1e-3) / 1e9], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        print(json.dumps({"probe": "plain 256 MB host-to-device copies" + (" + 32 MB device-to-host at the same time" if both else ""),
+                          "n_gpus": world, "input_gb_s_total": round(float(g.item()), 1)}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    sys.exit(0)
 cfg = lb.Config(nxcorr_threshold=0.96, min_variance=2.0, subpixel_step=0.1, consistency=True, max_lr_diff=1)
 host = []
 for f in range(FRAMES):
