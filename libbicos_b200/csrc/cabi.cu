@@ -1124,9 +1124,15 @@ int bicos_b200_match_host_begin(bicos_b200_handle h, const void* const* host_pla
     char* const out_disp = static_cast<char*>(stage_disp ? h->pin_disp.ptr : host_disparity);
     char* const out_corr = static_cast<char*>(stage_corr ? h->pin_corr.ptr : host_corrmap);
 
-    // PROBE (temporary, tools/e2e_probe.py): BICOS_B200_HOST_PROBE contains "nocompute" and / or "nod2h"
+    // Diagnostic build only (-DBICOS_B200_HOST_PROBE, tools/e2e_probe.py): the environment variable of the same name
+    // takes the kernels ("nocompute") and / or the result downloads ("nod2h") out of the pipeline, to see which part
+    // of the host link a many-GPU job loses where (profiles/r02_e2e_probe_n8.jsonl). Compiled out of the product.
+#ifdef BICOS_B200_HOST_PROBE
     static const char* probe = getenv("BICOS_B200_HOST_PROBE");
     const bool probe_nocompute = probe && strstr(probe, "nocompute"), probe_nod2h = probe && strstr(probe, "nod2h");
+#else
+    constexpr bool probe_nocompute = false, probe_nod2h = false;
+#endif
     // upload of band b is enqueued right before the match of band b, so the host never runs
     // far ahead of the device with copy submissions while kernels wait to be launched
     auto enqueue = [&]() -> int {
