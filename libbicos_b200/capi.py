@@ -16,7 +16,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libbicos_b200.so")
 
 DEPTH_8U, DEPTH_16U, TYPE_16S, TYPE_32F, TYPE_64F = 0, 2, 3, 5, 6
-FLAG_NODUPES, FLAG_CONSISTENCY, FLAG_TOP_BIT_FREE = 1, 2, 4
+FLAG_NODUPES, FLAG_CONSISTENCY, FLAG_TOP_BIT_FREE, FLAG_TOP2_BITS_FREE = 1, 2, 4, 8
 MAX_IMAGES = 65
 
 EXPORTS = (
@@ -231,13 +231,15 @@ class Handle:
                                           desc.data_ptr(), pitch_words, self._stream()))
         return desc, k
 
-    def search(self, desc0, desc1, k: int, cols: int, flags: int, top_bit_free: bool = False):
+    def search(self, desc0, desc1, k: int, cols: int, flags: int, top_bit_free=False):
         """Row-wise search on pitched descriptors -> (fwd_first, fwd_last, rev_first, rev_last).
 
         Each is a [rows, cols] int32 tensor holding uint32 keys cost << 16 | column (see
         include/bicos_b200.h), or None when `flags` does not need it. ``top_bit_free``: the caller
         vouches that bit 32k-1 of every descriptor is zero (BICOS_B200_FLAG_TOP_BIT_FREE; true for
-        transform() output), which lets the tensor-core engine use its column-term kernels."""
+        transform() output), which lets the tensor-core engine use its column-term kernels; ``top_bit_free=2``: the
+        top TWO bits are zero (BICOS_B200_FLAG_TOP2_BITS_FREE; also true for transform() output), which adds the
+        one-pass consistency kernel."""
         import torch
 
         rows, pitch_words = desc0.shape
@@ -252,7 +254,8 @@ class Handle:
         revl = keys(flags == (FLAG_NODUPES | FLAG_CONSISTENCY))
         ptr = [t.data_ptr() if t is not None else None for t in (fwdf, fwdl, revf, revl)]
         _check(lib().bicos_b200_search(self._h, desc0.data_ptr(), desc1.data_ptr(), k, rows, cols, pitch_words,
-                                       flags | (FLAG_TOP_BIT_FREE if top_bit_free else 0), *ptr, self._stream()))
+                                       flags | (FLAG_TOP2_BITS_FREE if int(top_bit_free) >= 2 else FLAG_TOP_BIT_FREE if top_bit_free else 0),
+                                       *ptr, self._stream()))
         return fwdf, fwdl, revf, revl
 
     def _outputs(self, cfg: Config, rows: int, cols: int, device):

@@ -551,7 +551,7 @@ int enqueue_search_stage(bicos_b200_handle h, const Unit& u, const MatchShape& s
     if (search_needs_prefill(sh.K, sh.cols)) // the popcount engine merges with atomicMin; the tensor-core engine stores every key
         CU(cudaMemsetAsync(keys, 0xFF, px * sizeof(uint32_t) * key_arrays(sh.flags), stream));
     // descriptors of our own transform: 4n - 6 or n^2 - 2n + 3 bits, never all 32 K, so the top bit is free
-    CU(launch_search(d0, d1, sh.K, u.nrows, sh.cols, dpw, sh.flags, ka.fwd_first, ka.fwd_last, ka.rev_first, ka.rev_last, stream, true));
+    CU(launch_search(d0, d1, sh.K, u.nrows, sh.cols, dpw, sh.flags, ka.fwd_first, ka.fwd_last, ka.rev_first, ka.rev_last, stream, 2)); // the transform leaves the top two descriptor bits clear
     h->launches += 1;
     return timer.end();
 }
@@ -834,9 +834,9 @@ int bicos_b200_search(bicos_b200_handle h, const uint32_t* desc0, const uint32_t
         return fail(BICOS_B200_ERR_INVALID, "null argument");
     if (K != 1 && K != 2 && K != 4 && K != 8 && K != 12 && K != 16)
         return fail(BICOS_B200_ERR_INVALID, "K must be 1, 2, 4 or 8 (12 or 16 for wide descriptors)");
-    if (flags < 0 || flags > 7)
+    if (flags < 0 || flags > 15)
         return fail(BICOS_B200_ERR_INVALID, "bad flags");
-    const bool top_bit_free = (flags & BICOS_B200_FLAG_TOP_BIT_FREE) != 0;
+    const int free_top_bits = (flags & BICOS_B200_FLAG_TOP2_BITS_FREE) ? 2 : (flags & BICOS_B200_FLAG_TOP_BIT_FREE) ? 1 : 0;
     flags &= 3;
     if (rows <= 0 || cols <= 0 || cols > 32767)
         return fail(BICOS_B200_ERR_INVALID, "bad image size");
@@ -859,7 +859,7 @@ int bicos_b200_search(bicos_b200_handle h, const uint32_t* desc0, const uint32_t
                 CU(cudaMemsetAsync(rev_last, 0xFF, bytes, s));
         }
     }
-    CU(launch_search(desc0, desc1, K, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, s, top_bit_free));
+    CU(launch_search(desc0, desc1, K, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, s, free_top_bits));
     h->launches += 1;
     return 0;
 }

@@ -89,7 +89,7 @@ cudaError_t launch_search(
     uint32_t* rev_first,
     uint32_t* rev_last,
     cudaStream_t stream,
-    bool top_bit_free = false
+    int free_top_bits = 0
 );
 
 // The two engines behind launch_search. `popc` (search.cu): XOR + POPC on the integer pipes, any
@@ -124,7 +124,9 @@ cudaError_t launch_search_mma(
     uint32_t* rev_first,
     uint32_t* rev_last,
     cudaStream_t stream,
-    bool top_bit_free = false // bit 32 K - 1 is zero in every descriptor (true for the transform's output)
+    int free_top_bits = 0 // how many of the top bits (32 K - 1, 32 K - 2) are zero in every descriptor: the transform's
+                          // output has 2 (4n-6 <= 32K-2; n^2-2n+3 mod 32 <= 27); 1 enables the column-term kernels, 2 the
+                          // one-pass consistency kernel as well
 );
 bool search_mma_colterm(); // see search_mma.cu, fold32
 void set_search_mma_colterm(bool on);

@@ -583,11 +583,11 @@ cudaError_t launch_search(
     uint32_t* rev_first,
     uint32_t* rev_last,
     cudaStream_t stream,
-    bool top_bit_free
+    int free_top_bits
 ) {
     const int engine = search_engine();
     if (engine == 2 || (engine == 0 && search_mma_supports(K, cols)))
-        return launch_search_mma(desc0, desc1, K, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, stream, top_bit_free);
+        return launch_search_mma(desc0, desc1, K, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, stream, free_top_bits);
     return launch_search_popc(desc0, desc1, K, rows, cols, desc_pitch_words, flags, fwd_first, fwd_last, rev_first, rev_last, stream);
 }
 

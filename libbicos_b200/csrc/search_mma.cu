@@ -1126,6 +1126,398 @@ teardown:
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// One-pass consistency search (128-bit descriptors, Consistency without no_dupes: the metric configuration).
+// The two kernels above compute the W x W Hamming matrix of a row twice, once per direction, because a
+// minimum ACROSS the TMEM lanes of one accumulator costs a cross-lane reduction per column. Here every pair
+// is computed once (SURVEY 8d's count) and both minima are taken from the same accumulator:
+//   work item   = (row, block of 128 RIGHT pixels): the block is the B operand, expanded once per item into
+//                 shared memory (signed bytes); the LEFT row streams past it as A operands, 128 pixels per
+//                 tile, expanded by the producer warps straight into tensor memory (tcgen05.st; unsigned bytes,
+//                 one LOP3 per four bytes), so an MMA reads only the 16 KB block from shared memory
+//   accumulator = D[lane = left pixel of the tile][column = right pixel of the block]
+//               = 128 * ham + column: both operands' top two descriptor bits are unused (4n-6 <= 32K-2,
+//                 n^2-2n+3 mod 32 <= 27), and their operand bytes carry 1 x column (as the CT kernels) and
+//                 128 x popc(right descriptor), which cancels the -128 popc of the signed operand
+//   forward     (per left pixel, minimum over the right row): in-thread fold over the 128 columns
+//                 (VIMNMX3.S16x2, four columns per instruction), merged over the blocks of the row by
+//                 atomicMin on the key array (pre-filled by the launcher)
+//   reverse     (per right pixel, minimum over the left row): ELEMENTWISE across the tiles of the item:
+//                 R[column] = min(R[column], D + tile) with the tile index as the tie-breaker
+//                 (VIADDMNMX.S16x2, two columns per instruction, no cross-lane traffic while the row streams);
+//                 one cross-lane reduction per ITEM (through shared memory, with the lane as the last
+//                 tie-breaker) instead of one per tile
+// A repeated last pixel pads ragged tiles and blocks: it ties with the real pixel and loses on the index.
+//   warps 0-3 / 4-7  epilogue of the even / odd tiles (global tile counter; the four lane quadrants each)
+//   warps 8-11       producers      warps 12, 13  MMA issuers (even / odd tiles)      warp 14  loader      warp 15  idle
+// TMEM: three 128-column accumulators in rotation (columns 0..383), four A tiles of 32 columns (384..511).
+constexpr int V3_THREADS = 512;
+constexpr int V3_REGS_LAUNCH = 104;
+constexpr int V3_REGS_EPILOGUE = 168; // 64 running minima + 64 accumulator registers
+constexpr int V3_REGS_PRODUCER = 40;
+constexpr int V3_REGS_ISSUER = 40;
+static_assert(256 * V3_REGS_EPILOGUE + 128 * V3_REGS_PRODUCER + 128 * V3_REGS_ISSUER <= V3_THREADS * V3_REGS_LAUNCH, "register budget");
+constexpr int V3_ASLOTS = 4;
+constexpr int V3_PACKED = 4;
+constexpr uint32_t V3_A_COL0 = 3 * TN;
+constexpr int V3_PACKED_BYTES = TN * 16;
+constexpr int V3_STATE_STRIDE = 132; // words per (epilogue group, column pair) row of 128 lanes: conflict-free LDS.128
+constexpr int V3_STATE_BYTES = 2 * 64 * V3_STATE_STRIDE * 4;
+constexpr int V3_FIN_BYTES = 4 * TN * 4;
+constexpr int V3_SMEM_BYTES = 2 * ATOM_BYTES + V3_PACKED * V3_PACKED_BYTES + V3_STATE_BYTES + V3_FIN_BYTES + 1024;
+// instruction descriptor: D = s32, A = unsigned int8 (the streamed left tile), B = signed int8 (the block)
+constexpr uint32_t IDESC3 = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ void tc_store8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t a) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// One left pixel -> its TMEM lane of A slot `taddr`: b * 2^s bytes, TMEM column 8 wi + s = bytes of bits s, 8 + s,
+// 16 + s, 24 + s of word wi. The bytes of the two unused top bits (word 3, byte 3, s = 6 / 7) are 128 and 1.
+__device__ __forceinline__ void expand_moving_to_tmem(const uint4& d, uint32_t taddr) {
+    const uint32_t w[4] = { d.x, d.y, d.z, d.w };
+#pragma unroll
+    for (int wi = 0; wi < 4; ++wi) {
+        uint32_t v[8];
+        v[0] = expand_word<true, 0>(w[wi]);
+        v[1] = expand_word<true, 1>(w[wi]);
+        v[2] = expand_word<true, 2>(w[wi]);
+        v[3] = expand_word<true, 3>(w[wi]);
+        v[4] = expand_word<true, 4>(w[wi]);
+        v[5] = expand_word<true, 5>(w[wi]);
+        v[6] = expand_word<true, 6>(w[wi]);
+        v[7] = expand_word<true, 7>(w[wi]);
+        if (wi == 3) {
+            v[6] |= 128u << 24;
+            v[7] |= 1u << 24;
+        }
+        tc_store8(taddr + 8u * wi, v);
+    }
+    tc_store_wait();
+}
+
+// One right pixel -> row r of the block tile in shared memory: (1 - 2b) * 2^(7 - s) bytes (128B-swizzled K-major, as
+// expand_pixel). The bytes of the two unused top bits carry popc(descriptor) (against the 128 of the left operand)
+// and the block column r (against the 1).
+__device__ __forceinline__ void expand_block_pixel(const uint4& d, uint32_t tile, int r) {
+    const uint32_t row = tile + (uint32_t)r * 128u;
+    const uint32_t sw = (uint32_t)(r & 7);
+    const uint32_t w[4] = { d.x, d.y, d.z, d.w };
+    const uint32_t pc = (uint32_t)(__popc(d.x) + __popc(d.y) + __popc(d.z) + __popc(d.w));
+#pragma unroll
+    for (int wi = 0; wi < 4; ++wi) {
+        st_shared_v4(row + ((((uint32_t)(2 * wi)) ^ sw) << 4), expand_word<false, 0>(w[wi]), expand_word<false, 1>(w[wi]),
+                     expand_word<false, 2>(w[wi]), expand_word<false, 3>(w[wi]));
+        uint32_t s6 = expand_word<false, 6>(w[wi]), s7 = expand_word<false, 7>(w[wi]);
+        if (wi == 3) {
+            s6 = (s6 & 0x00FFFFFFu) | (pc << 24);
+            s7 = (s7 & 0x00FFFFFFu) | ((uint32_t)r << 24);
+        }
+        st_shared_v4(row + ((((uint32_t)(2 * wi + 1)) ^ sw) << 4), expand_word<false, 4>(w[wi]), expand_word<false, 5>(w[wi]), s6, s7);
+    }
+}
+
+#define V3_ROLE_CONTEXT \
+    uint32_t fresh; \
+    asm volatile("mov.u32 %0, 0;" : "=r"(fresh)); \
+    const uint32_t tmem = *(volatile uint32_t*)&tmem_base_slot + fresh; \
+    const int cols = p.cols; \
+    const int ntiles = p.ntiles; /* left tiles per item = right blocks per row */ \
+    const long long item0 = p.items * (blockIdx.x + fresh) / gridDim.x; \
+    const int nitems = (int)(p.items * (blockIdx.x + fresh + 1) / gridDim.x - item0); \
+    const uint32_t s_blk = ((smem_u32(smem_raw) + fresh) + 1023u) & ~1023u; \
+    const uint32_t s_packed = s_blk + 2 * ATOM_BYTES; \
+    const uint32_t s_state = s_packed + V3_PACKED * V3_PACKED_BYTES; \
+    const uint32_t s_fin = s_state + V3_STATE_BYTES; \
+    const uint32_t bar_packed_full = smem_u32(&bars[0]) + fresh; \
+    const uint32_t bar_packed_free = bar_packed_full + 8 * V3_PACKED; \
+    const uint32_t bar_a_full = bar_packed_free + 8 * V3_PACKED; \
+    const uint32_t bar_a_free = bar_a_full + 8 * V3_ASLOTS; \
+    const uint32_t bar_blk_full = bar_a_free + 8 * V3_ASLOTS; \
+    const uint32_t bar_blk_free = bar_blk_full + 16; \
+    const uint32_t bar_acc_full = bar_blk_free + 16; \
+    const uint32_t bar_acc_drained = bar_acc_full + 48; \
+    const uint32_t bar_epi = bar_acc_drained + 48; \
+    int row = (int)(item0 / ntiles), nb = (int)(item0 - (long long)row * ntiles); \
+    (void)tmem, (void)cols, (void)s_blk, (void)s_packed, (void)s_state, (void)s_fin, (void)bar_packed_full, (void)bar_packed_free, (void)bar_a_full, \
+        (void)bar_a_free, (void)bar_blk_full, (void)bar_blk_free, (void)bar_acc_full, (void)bar_acc_drained, (void)bar_epi, (void)row, (void)nb;
+
+__global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) {
+    constexpr int NS = V3_ASLOTS;
+    constexpr int NP = V3_PACKED;
+    extern __shared__ uint8_t smem_raw[];
+    // packed full [NP], packed free [NP], A full [NS], A free [NS], block full [2], block free [2],
+    // accumulator full [3][2], drained [3][2] (per accumulator and epilogue group, see search_mma2_kernel), epilogue sync
+    __shared__ uint64_t bars[2 * NP + 2 * NS + 4 + 12 + 1];
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ Watch s_watch;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+
+    if (tid == 0) {
+        const uint32_t bar0 = smem_u32(&bars[0]);
+        s_watch.flag = p.timeout_flag;
+        s_watch.timeout_ns = p.timeout_ns;
+        s_watch.abort = 0;
+        for (int s = 0; s < NP; ++s) {
+            mbar_init(bar0 + 8 * s, 1); // packed full
+            mbar_init(bar0 + 8 * (NP + s), TM); // packed free
+        }
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(bar0 + 8 * (2 * NP + s), TM); // A full
+            mbar_init(bar0 + 8 * (2 * NP + NS + s), 1); // A free
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar0 + 8 * (2 * NP + 2 * NS + b), TN); // block full
+            mbar_init(bar0 + 8 * (2 * NP + 2 * NS + 2 + b), 2); // block free: both issuers
+        }
+        for (int a = 0; a < 6; ++a) {
+            mbar_init(bar0 + 8 * (2 * NP + 2 * NS + 4 + a), 1); // accumulator full
+            mbar_init(bar0 + 8 * (2 * NP + 2 * NS + 10 + a), TM); // accumulator drained
+        }
+        mbar_init(bar0 + 8 * (2 * NP + 2 * NS + 16), 2 * TM); // epilogue sync
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp >= 12) {
+        regs_shrink<V3_REGS_ISSUER>();
+        V3_ROLE_CONTEXT
+    if (warp == 15) {
+        // idle: setmaxnreg works on warpgroups
+    } else if (warp == 12 || warp == 13) {
+        // ---- MMA issuers: warp 12 + h issues the tiles with (global tile counter) & 1 == h ----
+        {
+            const int h = warp - 12;
+            const uint32_t u_tmem = uniform(tmem);
+            const uint64_t desc_b0 = smem_desc(uniform(s_blk));
+            constexpr uint32_t BLOCK_STEP = ATOM_BYTES >> 4;
+            int q = 0;
+            for (int n = 0; n < nitems; ++n) {
+                const uint32_t b = (uint32_t)n & 1u;
+                if (!mbar_wait(bar_blk_full + 8 * b, ((uint32_t)n >> 1) & 1u, &s_watch))
+                    goto teardown;
+                const uint64_t desc_b = desc_b0 + b * BLOCK_STEP;
+                for (int t = 0; t < ntiles; ++t, ++q) {
+                    if ((q & 1) != h)
+                        continue;
+                    const uint32_t a = (uint32_t)q % 3u;
+                    const uint32_t s = (uint32_t)q % (uint32_t)NS;
+                    if (!mbar_wait(bar_a_full + 8 * s, ((uint32_t)q / (uint32_t)NS) & 1u, &s_watch))
+                        goto teardown;
+                    if (q >= 3) // the accumulator's previous tile, read by the other epilogue group
+                        if (!mbar_wait(bar_acc_drained + 8 * (2 * a + (1 - h)), (((uint32_t)q - 3u) / 6u) & 1u, &s_watch))
+                            goto teardown;
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            tc_mma_i8_ts(u_tmem + a * TN, u_tmem + V3_A_COL0 + s * 32u + (uint32_t)(kk * 8), desc_b + (uint32_t)((kk * 32) >> 4),
+                                         IDESC3, kk != 0);
+                        tc_commit(bar_acc_full + 8 * (2 * a + h));
+                        tc_commit(bar_a_free + 8 * s);
+                    }
+                    __syncwarp();
+                }
+                // every MMA this warp issued on the block is complete when this arrives (counts 2: both issuers)
+                if (elect_one())
+                    tc_commit(bar_blk_free + 8 * b);
+                __syncwarp();
+            }
+        }
+    } else if (warp == 14) {
+        // ---- loader: per item the packed right block, then the packed left tiles of the row ----
+        if (tid == 14 * 32) {
+            int f = 0;
+            for (int n = 0; n < nitems; ++n) {
+                const uint32_t* const lrow = p.left + (size_t)row * p.pitch_words;
+                const uint32_t* const rrow = p.right + (size_t)row * p.pitch_words;
+                for (int e = 0; e <= ntiles; ++e, ++f) {
+                    const int s = f % NP;
+                    if (f >= NP)
+                        if (!mbar_wait(bar_packed_free + 8 * s, (f / NP - 1) & 1, &s_watch))
+                            goto teardown;
+                    const int base = (e == 0 ? nb : e - 1) * TN;
+                    const uint32_t bytes = (uint32_t)min(TN, cols - base) * 16u;
+                    mbar_expect_tx(bar_packed_full + 8 * s, bytes);
+                    bulk_copy_g2s(s_packed + (uint32_t)(s * V3_PACKED_BYTES), (e == 0 ? rrow : lrow) + (size_t)base * 4, bytes, bar_packed_full + 8 * s);
+                }
+                if (++nb == ntiles) {
+                    nb = 0;
+                    ++row;
+                }
+            }
+        }
+    }
+    } else if (warp >= 8) {
+        // ---- producers: ring entry 0 of an item = the right block -> shared memory (signed), entries 1.. = left tiles
+        //      -> tensor memory (unsigned). Thread r = row r of the block = TMEM lane r of the tile. ----
+        regs_shrink<V3_REGS_PRODUCER>();
+        V3_ROLE_CONTEXT
+        const int r = tid - 2 * TM;
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        int g = 0, q = 0;
+        for (int n = 0; n < nitems; ++n) {
+            for (int e = 0; e <= ntiles; ++e, ++g) {
+                const int ps = g % NP;
+                const int base = (e == 0 ? nb : e - 1) * TN;
+                const int valid = min(TN, cols - base);
+                if (!mbar_wait(bar_packed_full + 8 * ps, (g / NP) & 1, &s_watch))
+                    goto teardown;
+                const uint4 d = ld_shared_v4(s_packed + (uint32_t)(ps * V3_PACKED_BYTES) + (uint32_t)min(r, valid - 1) * 16u);
+                if (e == 0) {
+                    const uint32_t b = (uint32_t)n & 1u;
+                    if (n >= 2) // the MMAs of the item that used this buffer are complete
+                        if (!mbar_wait(bar_blk_free + 8 * b, (((uint32_t)n >> 1) - 1u) & 1u, &s_watch))
+                            goto teardown;
+                    expand_block_pixel(d, s_blk + b * ATOM_BYTES, r);
+                    mbar_arrive(bar_packed_free + 8 * ps); // after the stores that consumed the loaded registers
+                    fence_async_smem();
+                    mbar_arrive(bar_blk_full + 8 * b);
+                } else {
+                    const uint32_t s = (uint32_t)q % (uint32_t)NS;
+                    if (q >= NS)
+                        if (!mbar_wait(bar_a_free + 8 * s, ((uint32_t)q / (uint32_t)NS - 1u) & 1u, &s_watch))
+                            goto teardown;
+                    tc_fence_after();
+                    expand_moving_to_tmem(d, lane_base + V3_A_COL0 + s * 32u);
+                    mbar_arrive(bar_packed_free + 8 * ps);
+                    tc_fence_before();
+                    mbar_arrive(bar_a_full + 8 * s);
+                    ++q;
+                }
+            }
+            if (++nb == ntiles) {
+                nb = 0;
+                ++row;
+            }
+        }
+    } else {
+        // ---- epilogue: group h = warps 4h..4h+3 takes the tiles with (global tile counter) & 1 == h ----
+        regs_grow<V3_REGS_EPILOGUE>();
+        V3_ROLE_CONTEXT
+        const int h = warp >> 2;
+        const int lane128 = tid & (TM - 1);
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t R[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+            R[c] = 0x7FFF7FFFu;
+        uint32_t epi_phase = 0;
+        int q = 0;
+        for (int n = 0; n < nitems; ++n) {
+            const size_t row_at = (size_t)row * cols;
+            for (int t = 0; t < ntiles; ++t, ++q) {
+                if ((q & 1) != h)
+                    continue;
+                const int a = q % 3;
+                if (!mbar_wait(bar_acc_full + 8 * (2 * a + h), ((uint32_t)q / 6u) & 1u, &s_watch))
+                    goto teardown;
+                tc_fence_after();
+                const uint32_t acc = lane_base + (uint32_t)(a * TN);
+                int va[32], vb[32];
+                tc_load64_packed_issue(acc, va);
+                tc_load64_packed_issue(acc + 64, vb);
+                tc_load32_wait(va);
+                tc_load32_wait(vb);
+                tc_fence_before();
+                mbar_arrive(bar_acc_drained + 8 * (2 * a + h));
+                // forward: this left pixel's minimum of 128 ham + column over the block
+                TileMin16 m;
+                fold64_packed<false, 0, true>(va, m);
+                fold64_packed<false, 64, true>(vb, m);
+                const int v = min_of_lanes(m.f);
+                const int i = t * TM + lane128;
+                if (i < cols)
+                    atomicMin(p.fwd_first + row_at + i, ((uint32_t)(v >> 7) << 16) | (uint32_t)(nb * TN + (v & 127)));
+                // reverse: per column the minimum of 128 ham + column + tile over the tiles of this group
+                const uint32_t tile2 = (uint32_t)t * 0x00010001u;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    R[c] = __viaddmin_s16x2((uint32_t)va[c], tile2, R[c]);
+                    R[32 + c] = __viaddmin_s16x2((uint32_t)vb[c], tile2, R[32 + c]);
+                }
+            }
+            // ---- end of the item: the cross-lane reduction of both groups' running minima ----
+            {
+                const uint32_t dst = s_state + (uint32_t)((h * 64 * V3_STATE_STRIDE + lane128) * 4);
+#pragma unroll
+                for (int c = 0; c < 64; ++c) {
+                    st_shared_u32(dst + (uint32_t)(c * V3_STATE_STRIDE * 4), R[c]);
+                    R[c] = 0x7FFF7FFFu;
+                }
+                mbar_arrive(bar_epi);
+                if (!mbar_wait(bar_epi, epi_phase, &s_watch))
+                    goto teardown;
+                epi_phase ^= 1u;
+                // thread = (column pair cp, quarter c4): 64 lanes of one group's row of that pair
+                const int cp = tid & 63, c4 = tid >> 6;
+                const uint32_t src = s_state + (uint32_t)((((c4 >> 1) * 64 + cp) * V3_STATE_STRIDE + (c4 & 1) * 64) * 4);
+                uint32_t mlo = 0xFFFFFFFFu, mhi = 0xFFFFFFFFu;
+#pragma unroll
+                for (int l4 = 0; l4 < 16; ++l4) {
+                    const uint4 w = ld_shared_v4(src + 16u * l4);
+                    const uint32_t ww[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        mhi = min(mhi, (ww[k] & 0xFFFF0000u) + (uint32_t)(4 * l4 + k));
+                        mlo = min(mlo, (ww[k] << 16) + (uint32_t)(4 * l4 + k));
+                    }
+                }
+                const uint32_t lane0 = (uint32_t)(c4 & 1) * 64u;
+                st_shared_v2(s_fin + (uint32_t)((c4 * TN + 2 * cp) * 4), mlo + lane0, mhi + lane0);
+                mbar_arrive(bar_epi);
+                if (!mbar_wait(bar_epi, epi_phase, &s_watch))
+                    goto teardown;
+                epi_phase ^= 1u;
+                if (tid < TN) {
+                    const int col = nb * TN + tid;
+                    uint32_t k = min(min(ld_shared_u32(s_fin + (uint32_t)(tid * 4)), ld_shared_u32(s_fin + (uint32_t)((TN + tid) * 4))),
+                                     min(ld_shared_u32(s_fin + (uint32_t)((2 * TN + tid) * 4)), ld_shared_u32(s_fin + (uint32_t)((3 * TN + tid) * 4))));
+                    // k = (128 ham + column + tile) << 16 | lane
+                    const uint32_t v = (k >> 16) - (uint32_t)tid;
+                    if (col < cols)
+                        p.rev_first[row_at + col] = ((v >> 7) << 16) | ((v & 127u) * TM + (k & 0xFFFFu));
+                }
+            }
+            if (++nb == ntiles) {
+                nb = 0;
+                ++row;
+            }
+        }
+    }
+
+teardown:
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*(volatile uint32_t*)&tmem_base_slot), "r"(512u) : "memory");
+    }
+}
+
 int sm_count_of_current_device() {
     static thread_local int cached_dev = -1, cached_sms = 148;
     int dev = 0;
@@ -1209,6 +1601,23 @@ cudaError_t launch_k(MmaArgs p, int dirs, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+cudaError_t launch_k3(MmaArgs p, cudaStream_t stream) {
+    auto kernel = search_mma3_kernel;
+    cudaError_t err = configure_once(kernel, V3_SMEM_BYTES);
+    if (err != cudaSuccess)
+        return err;
+    p.items = (long long)p.rows * p.ntiles; // (row, block of 128 right pixels)
+    if (p.items > 0x7FFFFFFFLL)
+        return cudaErrorInvalidConfiguration;
+    // the forward keys of a row are merged over its blocks with atomicMin
+    if ((err = cudaMemsetAsync(p.fwd_first, 0xFF, (size_t)p.rows * p.cols * sizeof(uint32_t), stream)) != cudaSuccess)
+        return err;
+    const int sms = sm_count_of_current_device();
+    const unsigned grid = (unsigned)(p.items < sms ? p.items : sms);
+    kernel<<<grid, V3_THREADS, V3_SMEM_BYTES, stream>>>(p);
+    return cudaGetLastError();
+}
+
 } // namespace
 
 int search_mma_smem_bytes(int K) {
@@ -1273,7 +1682,8 @@ unsigned int search_mma_take_timeout() {
 }
 
 // 1 = two CTAs per SM, both operands in shared memory; 2 = one CTA per SM, left operand in tensor memory
-// (128 / 256 bits); 0 = automatic: 2 where it applies and the image has an item for every SM (measured on
+// (128 / 256 bits); 3 = the one-pass consistency kernel (128 bits, Consistency without no_dupes, two free top bits);
+// 0 = automatic: 3 where it applies, else 2 where it applies and the image has an item for every SM (measured on
 // the B200: 1.25 against 1.34 ms on the metric configuration, 2.35 against 2.63 ms for 256 bits x 4096
 // columns; small images are served better by the finer items of variant 1). Environment
 // BICOS_B200_MMA_VARIANT = 1 | 2 overrides for A/B timing.
@@ -1281,14 +1691,14 @@ int search_mma_variant() {
     int g = g_variant.load(std::memory_order_relaxed);
     if (g < 0) {
         const char* v = getenv("BICOS_B200_MMA_VARIANT");
-        g = v && v[0] == '2' ? 2 : v && v[0] == '1' ? 1 : 0;
+        g = v && v[0] == '3' ? 3 : v && v[0] == '2' ? 2 : v && v[0] == '1' ? 1 : 0;
         g_variant.store(g, std::memory_order_relaxed);
     }
     return g;
 }
 
 void set_search_mma_variant(int v) {
-    g_variant.store(v == 2 ? 2 : v == 1 ? 1 : 0, std::memory_order_relaxed);
+    g_variant.store(v >= 1 && v <= 3 ? v : 0, std::memory_order_relaxed);
 }
 
 // Whether descriptors with a free top bit take the column-term kernels (fold32): environment
@@ -1324,8 +1734,9 @@ cudaError_t launch_search_mma(
     uint32_t* rev_first,
     uint32_t* rev_last,
     cudaStream_t stream,
-    bool top_bit_free
+    int free_top_bits
 ) {
+    const bool top_bit_free = free_top_bits >= 1;
     if (rows <= 0 || !search_mma_supports(K, cols))
         return cudaErrorInvalidValue;
     if ((((uintptr_t)desc0 | (uintptr_t)desc1) & 15) != 0 || (desc_pitch_words & 3) != 0)
@@ -1348,6 +1759,11 @@ cudaError_t launch_search_mma(
     const bool nodupes = (flags & FLAG_NODUPES) != 0;
     const long long pair_items = (long long)dirs * rows * ((cols + 2 * TM - 1) / (2 * TM));
     const int variant = search_mma_variant();
+    // one product for both directions: 128-bit descriptors whose top TWO bits are free, Consistency without no_dupes
+    if (K == 4 && flags == FLAG_CONSISTENCY && free_top_bits >= 2 && (variant == 3 || variant == 0) && search_mma_colterm()) {
+        note_search_kernel("mma3<K=4,nodupes=0,ct=2,onepass=1>");
+        return launch_k3(p, stream);
+    }
     const bool v2 = (K == 4 || K == 8) && (variant == 2 || (variant == 0 && pair_items >= 2 * sm_count_of_current_device()));
     // column term through the MMA (see fold32): only where the caller vouches for the free top bit
     const bool ct = top_bit_free && (K == 4 || K == 8) && search_mma_colterm();

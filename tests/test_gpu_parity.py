@@ -179,15 +179,18 @@ def test_match_float_parity(handle, oracles, n, dtype, rows, cols, kw):
     assert both.mean() > 0.2 or n <= 5, "test scene should have valid matches"
 
 
-# The kernels behind the headline numbers: variant 2 of the tensor-core search (one CTA per SM, left operand in
-# TMEM) is only dispatched when the image has at least two (direction, row, 256-pixel) items per SM, and the
-# column-term form only through bicos_b200_match. These scenes are large enough for both and small enough for the
+# The kernels behind the headline numbers: the one-pass consistency kernel (128-bit descriptors, Consistency without
+# no_dupes) needs the two free top bits only bicos_b200_match vouches for; variant 2 of the two-pass search (one CTA
+# per SM, left operand in TMEM) is only dispatched when the image has at least two (direction, row, 256-pixel) items
+# per SM, and the column-term form only through bicos_b200_match. These scenes are large enough for both and small enough for the
 # oracle; bicos_b200_last_search_kernel() proves which kernel ran, so a change of the dispatch rule cannot
 # silently take them out of the suite.
 BENCHED = [
     # n, dtype, rows, cols, config, kernel expected on a 148-SM B200
     (33, np.uint8, 160, 512, dict(nxcorr_threshold=0.96, min_variance=2.0, subpixel_step=0.1, consistency=True, max_lr_diff=1),
-     "mma2<K=4,nodupes=0,ct=1,dirs=2>"),  # the bench workload's configuration
+     "mma3<K=4,nodupes=0,ct=2,onepass=1>"),  # the bench workload's configuration: the one-pass consistency kernel
+    (33, np.uint8, 131, 700, dict(nxcorr_threshold=0.9, subpixel_step=0.25, consistency=True, max_lr_diff=0), "mma3<K=4,nodupes=0,ct=2,onepass=1>"),  # ragged tile and block
+    (12, np.uint8, 140, 640, dict(nxcorr_threshold=0.9, mode_full=True, consistency=True, max_lr_diff=2), "mma3<K=4,nodupes=0,ct=2,onepass=1>"),  # FULL, 123 of 128 bits
     (33, np.uint8, 152, 520, dict(nxcorr_threshold=0.96, min_variance=2.0), "mma2<K=4,nodupes=1,ct=1,dirs=1>"),  # C1, ragged last tile
     (33, np.uint8, 160, 512, dict(nxcorr_threshold=0.9, subpixel_step=0.25, consistency=True, max_lr_diff=2, no_dupes=True),
      "mma2<K=4,nodupes=1,ct=1,dirs=2>"),
@@ -325,14 +328,15 @@ def test_search_wide_rows_split_units(handle, oracles, engine, k, cols, flags):
 @pytest.mark.parametrize("k,rows,cols,flags", [(4, 700, 384, 3), (4, 40, 2048, 2), (8, 500, 300, 1), (8, 12, 2448, 3),
                                                (12, 330, 256, 2), (16, 310, 200, 3), (4, 1300, 130, 0), (4, 90, 1000, 2),
                                                (8, 200, 520, 2)])
-@pytest.mark.parametrize("top_bit_free", [False, True])
+@pytest.mark.parametrize("top_bit_free", [False, True, 2])
 def test_search_engines_identical(handle, oracles, k, rows, cols, flags, top_bit_free):
     """The tensor-core engine (int8 GEMM + argmin epilogue) reproduces the popcount engine's four key arrays bit
     for bit, at sizes where a persistent CTA walks several work items (rows x M tiles x directions > resident CTAs)
     and with descriptors drawn from a small pool, so that exact ties are the rule. With `top_bit_free` the top
     descriptor bit is clear and the tensor-core engine is told so (BICOS_B200_FLAG_TOP_BIT_FREE): the column-term
-    kernels bicos_b200_match uses, in both kernel variants. The postfiltered disparity of the tensor-core keys is
-    also compared with the oracle's bicos()."""
+    kernels bicos_b200_match uses, in both kernel variants; with top_bit_free = 2 the top two bits are clear
+    (BICOS_B200_FLAG_TOP2_BITS_FREE) and 128-bit consistency searches take the one-pass kernel. The postfiltered
+    disparity of the tensor-core keys is also compared with the oracle's bicos()."""
     import torch
 
     rng = np.random.default_rng(k + rows + cols + flags)
@@ -341,12 +345,12 @@ def test_search_engines_identical(handle, oracles, k, rows, cols, flags, top_bit
     def draw():
         d = pool[rng.integers(0, len(pool), size=(rows, cols))]
         flip = rng.integers(0, 4, size=(rows, cols, 1)) > 1
-        bit = rng.integers(0, 32 * k - 1, size=(rows, cols))
+        bit = rng.integers(0, 32 * k - 2, size=(rows, cols))
         mask = np.zeros((rows, cols, k), dtype=np.uint32)
         np.put_along_axis(mask, (bit // 32)[..., None], (np.uint32(1) << (bit % 32).astype(np.uint32))[..., None], axis=2)
         d = d ^ (mask * flip)
         if top_bit_free:
-            d[..., k - 1] &= np.uint32(0x7FFFFFFF)
+            d[..., k - 1] &= np.uint32(0x3FFFFFFF if top_bit_free == 2 else 0x7FFFFFFF)
         return d
 
     pitch = (cols * k + 3) // 4 * 4
@@ -368,8 +372,11 @@ def test_search_engines_identical(handle, oracles, k, rows, cols, flags, top_bit
             assert kernel.startswith("popc<" if name == "popc" else "mma"), kernel
     finally:
         lb.set_search_engine("auto")
-    assert f"ct={int(top_bit_free and k in (4, 8))}" in kernel, kernel
-    if torch.cuda.get_device_properties(0).multi_processor_count == 148:
+    onepass = top_bit_free == 2 and k == 4 and flags == FLAG_CONSISTENCY
+    assert f"ct={2 if onepass else int(bool(top_bit_free) and k in (4, 8))}" in kernel, kernel
+    if onepass:
+        assert kernel.startswith("mma3<"), kernel
+    elif torch.cuda.get_device_properties(0).multi_processor_count == 148:
         dirs = 2 if flags & FLAG_CONSISTENCY else 1
         v2 = k in (4, 8) and dirs * rows * ((cols + 255) // 256) >= 296
         assert kernel.startswith("mma2<" if v2 else "mma1<"), kernel
@@ -550,7 +557,7 @@ def test_match_batch_equals_single_matches(handle, oracles):
     torch.cuda.synchronize()
     for rep in range(3):
         outs = handle.match_batch(frames, cfg)
-        assert lb.last_search_kernel() == "mma2<K=4,nodupes=0,ct=1,dirs=2>" or torch.cuda.get_device_properties(0).multi_processor_count != 148
+        assert lb.last_search_kernel() == "mma3<K=4,nodupes=0,ct=2,onepass=1>"
         # stream-ordered: consuming the results on the current stream needs no synchronisation of our own
         for (d, c), (sd, sc) in zip(outs, single):
             assert torch.equal(torch.nan_to_num(d, nan=-9.0), torch.nan_to_num(sd, nan=-9.0))
@@ -579,7 +586,7 @@ def test_match_batch_equals_single_matches(handle, oracles):
 
 @pytest.mark.parametrize("n,dtype,full,rows,cols,kw", [
     (33, np.uint8, False, 7, 300, dict(nxcorr_threshold=0.9, subpixel_step=0.25, consistency=True, max_lr_diff=1, no_dupes=True)),
-    (33, np.uint8, False, 150, 513, dict(nxcorr_threshold=0.9, subpixel_step=0.5, consistency=True)),  # search_mma2, ragged tiles
+    (33, np.uint8, False, 150, 513, dict(nxcorr_threshold=0.9, subpixel_step=0.5, consistency=True)),  # one-pass search, ragged tiles
     (64, np.uint8, False, 150, 300, dict(nxcorr_threshold=0.9)),  # search_mma2, 256 bits
     (16, np.uint16, True, 5, 131, dict(nxcorr_threshold=0.9, double=True, min_variance=1.0)),
     (9, np.uint8, False, 3, 1, dict(nxcorr_threshold=None)),  # 32-bit descriptors: popcount engine
@@ -628,7 +635,7 @@ def test_kernels_write_only_their_buffers(handle, n, dtype, full, rows, cols, kw
             keys = [guarded(px) for _ in range(4)]
             flags = cfg.flags
             ptrs = [keys[0][1], keys[1][1] if flags & 1 else None, keys[2][1] if flags & 2 else None, keys[3][1] if flags == 3 else None]
-            capi._check(L.bicos_b200_search(handle._h, d[0][1], d[1][1], k, rows, cols, pw, flags | capi.FLAG_TOP_BIT_FREE, *ptrs, st))
+            capi._check(L.bicos_b200_search(handle._h, d[0][1], d[1][1], k, rows, cols, pw, flags | capi.FLAG_TOP2_BITS_FREE, *ptrs, st))  # as bicos_b200_match: the transform's output
             disp_words = px if cfg.nxcorr_threshold is not None else (px + 1) // 2
             corr_words = px * (2 if cfg.double else 1)
             raw, disp, corr = guarded((px + 1) // 2), guarded(disp_words), guarded(corr_words)

@@ -142,3 +142,88 @@ def test_column_term_rides_in_the_top_bits_byte(k):
     assert np.array_equal(acc, 128 * (ham - popcount(left)[:, None]) + np.arange(TN)[None, :])
     if k == 4:
         assert np.abs(acc).max() + 127 < 2**15  # the last-minimum key adds 127 - 2u on top
+
+
+# ---- the one-pass consistency kernel (search_mma3_kernel): both directions from one accumulator ----
+
+def test_top_two_descriptor_bits_are_never_used():
+    """What free_top_bits = 2 (bicos_b200_match -> launch_search) promises for the one-pass kernel: bits 32K-1 and
+    32K-2 stay clear for every stack size the reference accepts."""
+    import oracle
+
+    for full, sizes in ((False, range(2, 66)), (True, range(2, 17))):
+        for n in sizes:
+            k = oracle.words_per_descriptor(n, full, False)
+            assert _used_bits(n, full) <= 32 * k - 2, (n, full, k)
+
+
+def _onepass_operands(left: np.ndarray, right_block: np.ndarray):
+    """A = the streamed LEFT tile as unsigned bytes (expand_moving_to_tmem), B = the RIGHT block as signed bytes
+    (expand_block_pixel); the bytes of the two unused top bits (word 3, byte 3, s = 6 / 7) carry 128 x popc(right) and
+    1 x block column."""
+    k = left.shape[1]
+    a, b = operands(left, False), operands(right_block, True)  # unsigned / signed encodings
+    pos6, pos7 = 32 * k - 5, 32 * k - 1  # (last word, s = 6, byte 3) and (last word, s = 7, byte 3) in (word, s, byte) order
+    assert np.all(a[:, pos6] == 0) and np.all(a[:, pos7] == 0) and np.all(b[:, pos6] == 2) and np.all(b[:, pos7] == 1)
+    a[:, pos6], a[:, pos7] = 128, 1
+    b[:, pos6], b[:, pos7] = popcount(right_block), np.arange(len(right_block))
+    assert a.min() >= 0 and a.max() <= 255 and b.min() >= -128 and b.max() <= 127  # u8 x s8
+    return a, b
+
+
+def test_onepass_accumulator_is_128_hamming_plus_block_column():
+    rng = np.random.default_rng(5)
+    left = rng.integers(0, 2**32, size=(128, 4), dtype=np.uint64).astype(np.uint32)
+    right = rng.integers(0, 2**32, size=(TN, 4), dtype=np.uint64).astype(np.uint32)
+    left[:, -1] &= 0x3FFFFFFF
+    right[:, -1] &= 0x3FFFFFFF
+    left[0], right[0] = 0, 0
+    left[1, :3], right[1, :3] = 0xFFFFFFFF, 0xFFFFFFFF
+    left[1, 3], right[2, 3] = 0x3FFFFFFF, 0x3FFFFFFF  # 126 set bits: the largest popcount byte
+    a, b = _onepass_operands(left, right)
+    acc = a @ b.T  # [left pixel = TMEM lane, right pixel = accumulator column]
+    ham = popcount(left[:, None, :] ^ right[None, :, :])
+    assert np.array_equal(acc, 128 * ham + np.arange(TN)[None, :])
+    assert acc.min() >= 0 and acc.max() + 127 < 2**15  # + tile index: still a positive signed half word
+
+
+@pytest.mark.parametrize("cols", [1, 97, 128, 300, 1000])
+def test_onepass_folds_give_both_first_minima(cols):
+    """Forward: per left pixel the minimum of 128 ham + block column over the columns of each block, merged over
+    the blocks as cost << 16 | column (atomicMin). Reverse: per right pixel the ELEMENTWISE minimum of
+    128 ham + column + tile over the left tiles (per TMEM lane), then the minimum over the lanes of
+    (that << 16) + lane: decodes to cost << 16 | first left column."""
+    rng = np.random.default_rng(1000 + cols)
+    pool = rng.integers(0, 2**32, size=(10, 4), dtype=np.uint64).astype(np.uint32)
+    pool[:, -1] &= 0x3FFFFFFF
+    left = pool[rng.integers(0, len(pool), size=cols)]
+    right = pool[rng.integers(0, len(pool), size=cols)] ^ ((rng.integers(0, 3, size=(cols, 1)) == 0) * np.uint32(1 << 5))
+    ham = popcount(left[:, None, :] ^ right[None, :, :]).astype(np.int64)  # [left, right]
+    tiles = (cols + TN - 1) // TN
+
+    def padded(d, t):  # a ragged tile / block repeats its last pixel
+        idx = np.minimum(np.arange(t * TN, (t + 1) * TN), cols - 1)
+        return d[idx]
+
+    fwd = np.full(cols, 0xFFFFFFFF, dtype=np.int64)
+    rev = np.zeros(cols, dtype=np.int64)
+    for nb in range(tiles):
+        running = np.full((TN, TN), 0x7FFF, dtype=np.int64)  # [lane, block column], one row per epilogue thread
+        for t in range(tiles):
+            a, b = _onepass_operands(padded(left, t), padded(right, nb))
+            acc = (a @ b.T).astype(np.int64)
+            v = acc.min(axis=1)  # in-thread fold: 128 ham + first column at that cost
+            i = t * TN + np.arange(TN)
+            key = ((v >> 7) << 16) | (nb * TN + (v & 127))
+            ok = i < cols
+            fwd[i[ok]] = np.minimum(fwd[i[ok]], key[ok])
+            running = np.minimum(running, acc + t)
+        k = ((running << 16) + np.arange(TN)[:, None]).min(axis=0)  # over the lanes
+        v = (k >> 16) - np.arange(TN)
+        col = nb * TN + np.arange(TN)
+        ok = col < cols
+        rev[col[ok]] = (((v >> 7) << 16) | ((v & 127) * TN + (k & 0xFFFF)))[ok]
+
+    best_f, best_r = ham.min(axis=1), ham.min(axis=0)
+    assert np.array_equal(fwd, (best_f << 16) | (ham == best_f[:, None]).argmax(axis=1))
+    assert np.array_equal(rev, (best_r << 16) | (ham == best_r[None, :]).argmax(axis=0))

@@ -33,7 +33,9 @@ int main(int argc, char** argv) {
     if (argc > 7)
         set_search_mma_variant(std::atoi(argv[7])); // else: default / BICOS_B200_MMA_VARIANT
     // COLTERM = 1: descriptors with a zero top bit (as the transform writes them) and the column-term kernels
-    const bool colterm = argc > 8 && std::atoi(argv[8]) != 0;
+    // COLTERM = 2: the top two bits are zero, which also admits the one-pass consistency kernel (variant 0 or 3)
+    const int free_bits = argc > 8 ? std::atoi(argv[8]) : 0;
+    const bool colterm = free_bits != 0;
     set_search_mma_colterm(colterm);
 
     const size_t pitch = ((size_t)cols * K + 3) / 4 * 4;
@@ -55,7 +57,7 @@ int main(int argc, char** argv) {
                     p[bit / 32] ^= 1u << (bit % 32);
                 }
                 if (colterm)
-                    p[K - 1] &= 0x7FFFFFFFu;
+                    p[K - 1] &= free_bits >= 2 ? 0x3FFFFFFFu : 0x7FFFFFFFu;
             }
     };
     std::vector<uint32_t> h0, h1;
@@ -80,7 +82,7 @@ int main(int argc, char** argv) {
         auto run = [&]() {
             return engine == 0
                 ? launch_search_popc(d0, d1, K, rows, cols, pitch, flags, k, k + px, k + 2 * px, k + 3 * px, 0)
-                : launch_search_mma(d0, d1, K, rows, cols, pitch, flags, k, k + px, k + 2 * px, k + 3 * px, 0, colterm);
+                : launch_search_mma(d0, d1, K, rows, cols, pitch, flags, k, k + px, k + 2 * px, k + 3 * px, 0, free_bits);
         };
         CK(cudaMemset(k, 0xFF, px * 16));
         CK(run());
@@ -125,8 +127,8 @@ int main(int argc, char** argv) {
             ties += (a[i] & 0xFFFF) != 65535u - (a[px + i] & 0xFFFF);
     const double pairs = (double)rows * cols * cols * ((flags & FLAG_CONSISTENCY) ? 1 : 1);
     std::printf(
-        "cols %d rows %d K %d flags %d variant %d colterm %d: popc %.4f ms (%.3f Tpair/s), mma %.4f ms (%.3f Tpair/s), speed-up %.2fx, forward ties %lld, %s\n",
-        cols, rows, K, flags, search_mma_variant(), (int)colterm, ms[0], pairs / ms[0] * 1e-9, ms[1], pairs / ms[1] * 1e-9, ms[1] > 0 ? ms[0] / ms[1] : 0.0, ties,
+        "cols %d rows %d K %d flags %d variant %d colterm %d [%s]: popc %.4f ms (%.3f Tpair/s), mma %.4f ms (%.3f Tpair/s), speed-up %.2fx, forward ties %lld, %s\n",
+        cols, rows, K, flags, search_mma_variant(), free_bits, last_search_kernel(), ms[0], pairs / ms[0] * 1e-9, ms[1], pairs / ms[1] * 1e-9, ms[1] > 0 ? ms[0] / ms[1] : 0.0, ties,
         bad_total ? "MISMATCH" : "identical"
     );
     return bad_total ? 1 : 0;
