@@ -1131,10 +1131,11 @@ teardown:
 // The two kernels above compute the W x W Hamming matrix of a row twice, once per direction, because a
 // minimum ACROSS the TMEM lanes of one accumulator costs a cross-lane reduction per column. Here every pair
 // is computed once (SURVEY 8d's count) and both minima are taken from the same accumulator:
-//   work item   = (row, block of 128 RIGHT pixels): the block is the B operand, expanded once per item into
-//                 shared memory (signed bytes); the LEFT row streams past it as A operands, 128 pixels per
-//                 tile, expanded by the producer warps straight into tensor memory (tcgen05.st; unsigned bytes,
-//                 one LOP3 per four bytes), so an MMA reads only the 16 KB block from shared memory
+//   work item   = (row, pair of blocks of 128 RIGHT pixels): each block is a B operand, expanded once per item
+//                 into shared memory (signed bytes); the LEFT row streams past them as A operands, 128 pixels
+//                 per tile, expanded by the producer warps straight into tensor memory (tcgen05.st; unsigned
+//                 bytes, one LOP3 per four bytes), so an MMA reads only its 16 KB block from shared memory and
+//                 every expanded tile serves two MMA groups (one per block)
 //   accumulator = D[lane = left pixel of the tile][column = right pixel of the block]
 //               = 128 * ham + column: both operands' top two descriptor bits are unused (4n-6 <= 32K-2,
 //                 n^2-2n+3 mod 32 <= 27), and their operand bytes carry 1 x column (as the CT kernels) and
@@ -1147,10 +1148,12 @@ teardown:
 //                 (VIADDMNMX.S16x2, two columns per instruction, no cross-lane traffic while the row streams);
 //                 one cross-lane reduction per ITEM (through shared memory, with the lane as the last
 //                 tie-breaker) instead of one per tile
-// A repeated last pixel pads ragged tiles and blocks: it ties with the real pixel and loses on the index.
-//   warps 0-3 / 4-7  epilogue of the even / odd tiles (global tile counter; the four lane quadrants each)
-//   warps 8-11       producers      warps 12, 13  MMA issuers (even / odd tiles)      warp 14  loader      warp 15  idle
-// TMEM: three 128-column accumulators in rotation (columns 0..383), four A tiles of 32 columns (384..511).
+// A repeated last pixel pads ragged tiles and blocks (and a missing second block): it ties with the real pixel
+// and loses on the index.
+//   warps 0-3 / 4-7  epilogue of block 0 / 1 (the four TMEM lane quadrants each)
+//   warps 8-11       producers      warps 12, 13  MMA issuers (block 0 / 1)      warp 14  loader      warp 15  idle
+// TMEM: three 128-column accumulators in rotation (columns 0..383, MMA group 2 g + h -> accumulator (2 g + h) % 3
+// as in search_mma2_kernel), four A tiles of 32 columns (384..511).
 constexpr int V3_THREADS = 512;
 constexpr int V3_REGS_LAUNCH = 104;
 constexpr int V3_REGS_EPILOGUE = 168; // 64 running minima + 64 accumulator registers
@@ -1161,10 +1164,10 @@ constexpr int V3_ASLOTS = 4;
 constexpr int V3_PACKED = 4;
 constexpr uint32_t V3_A_COL0 = 3 * TN;
 constexpr int V3_PACKED_BYTES = TN * 16;
-constexpr int V3_STATE_STRIDE = 132; // words per (epilogue group, column pair) row of 128 lanes: conflict-free LDS.128
-constexpr int V3_STATE_BYTES = 2 * 64 * V3_STATE_STRIDE * 4;
-constexpr int V3_FIN_BYTES = 4 * TN * 4;
-constexpr int V3_SMEM_BYTES = 2 * ATOM_BYTES + V3_PACKED * V3_PACKED_BYTES + V3_STATE_BYTES + V3_FIN_BYTES + 1024;
+constexpr int V3_STATE_STRIDE = 132; // words per column-pair row of 128 lanes: conflict-free LDS.128
+constexpr int V3_STATE_BYTES = 64 * V3_STATE_STRIDE * 4; // per epilogue group
+constexpr int V3_FIN_BYTES = 2 * TN * 4; // per epilogue group
+constexpr int V3_SMEM_BYTES = 4 * ATOM_BYTES + V3_PACKED * V3_PACKED_BYTES + 2 * V3_STATE_BYTES + 2 * V3_FIN_BYTES + 1024;
 // instruction descriptor: D = s32, A = unsigned int8 (the streamed left tile), B = signed int8 (the block)
 constexpr uint32_t IDESC3 = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
@@ -1172,6 +1175,17 @@ __device__ __forceinline__ void tc_store8(uint32_t taddr, const uint32_t (&v)[8]
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
                  "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
+}
+
+// 128 consecutive accumulator columns of this thread's lane, the low halves of columns 2r and 2r + 1 in register r
+__device__ __forceinline__ void tc_load128_packed(uint32_t taddr, uint32_t (&v)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        : "r"(taddr)
+        : "memory"
+    );
 }
 
 __device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
@@ -1184,6 +1198,12 @@ __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
+}
+// a value the compiler must keep in a register of its own (not re-derive from %tid inside a loop)
+__device__ __forceinline__ uint32_t pinned(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
 }
 
 // One left pixel -> its TMEM lane of A slot `taddr`: b * 2^s bytes, TMEM column 8 wi + s = bytes of bits s, 8 + s,
@@ -1236,33 +1256,35 @@ __device__ __forceinline__ void expand_block_pixel(const uint4& d, uint32_t tile
     asm volatile("mov.u32 %0, 0;" : "=r"(fresh)); \
     const uint32_t tmem = *(volatile uint32_t*)&tmem_base_slot + fresh; \
     const int cols = p.cols; \
-    const int ntiles = p.ntiles; /* left tiles per item = right blocks per row */ \
+    const int ntiles = p.ntiles; /* left tiles per item */ \
+    const int npairs = p.mtiles; /* pairs of right blocks per row */ \
     const long long item0 = p.items * (blockIdx.x + fresh) / gridDim.x; \
     const int nitems = (int)(p.items * (blockIdx.x + fresh + 1) / gridDim.x - item0); \
-    const uint32_t s_blk = ((smem_u32(smem_raw) + fresh) + 1023u) & ~1023u; \
-    const uint32_t s_packed = s_blk + 2 * ATOM_BYTES; \
-    const uint32_t s_state = s_packed + V3_PACKED * V3_PACKED_BYTES; \
-    const uint32_t s_fin = s_state + V3_STATE_BYTES; \
+    const uint32_t s_blk = ((smem_u32(smem_raw) + fresh) + 1023u) & ~1023u; /* + (2 buffer + block) * ATOM_BYTES */ \
+    const uint32_t s_packed = s_blk + 4 * ATOM_BYTES; \
+    const uint32_t s_state = s_packed + V3_PACKED * V3_PACKED_BYTES; /* + group * V3_STATE_BYTES */ \
+    const uint32_t s_fin = s_state + 2 * V3_STATE_BYTES; /* + group * V3_FIN_BYTES */ \
     const uint32_t bar_packed_full = smem_u32(&bars[0]) + fresh; \
     const uint32_t bar_packed_free = bar_packed_full + 8 * V3_PACKED; \
     const uint32_t bar_a_full = bar_packed_free + 8 * V3_PACKED; \
     const uint32_t bar_a_free = bar_a_full + 8 * V3_ASLOTS; \
-    const uint32_t bar_blk_full = bar_a_free + 8 * V3_ASLOTS; \
-    const uint32_t bar_blk_free = bar_blk_full + 16; \
-    const uint32_t bar_acc_full = bar_blk_free + 16; \
+    const uint32_t bar_blk_full = bar_a_free + 8 * V3_ASLOTS; /* + 8 * (2 buffer + block) */ \
+    const uint32_t bar_blk_free = bar_blk_full + 32; \
+    const uint32_t bar_acc_full = bar_blk_free + 32; \
     const uint32_t bar_acc_drained = bar_acc_full + 48; \
-    const uint32_t bar_epi = bar_acc_drained + 48; \
-    int row = (int)(item0 / ntiles), nb = (int)(item0 - (long long)row * ntiles); \
-    (void)tmem, (void)cols, (void)s_blk, (void)s_packed, (void)s_state, (void)s_fin, (void)bar_packed_full, (void)bar_packed_free, (void)bar_a_full, \
-        (void)bar_a_free, (void)bar_blk_full, (void)bar_blk_free, (void)bar_acc_full, (void)bar_acc_drained, (void)bar_epi, (void)row, (void)nb;
+    const uint32_t bar_epi = bar_acc_drained + 48; /* + 8 * group */ \
+    int row = (int)(item0 / npairs), bp = (int)(item0 - (long long)row * npairs); \
+    (void)tmem, (void)cols, (void)ntiles, (void)s_blk, (void)s_packed, (void)s_state, (void)s_fin, (void)bar_packed_full, (void)bar_packed_free, \
+        (void)bar_a_full, (void)bar_a_free, (void)bar_blk_full, (void)bar_blk_free, (void)bar_acc_full, (void)bar_acc_drained, (void)bar_epi, \
+        (void)row, (void)bp;
 
 __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) {
     constexpr int NS = V3_ASLOTS;
     constexpr int NP = V3_PACKED;
     extern __shared__ uint8_t smem_raw[];
-    // packed full [NP], packed free [NP], A full [NS], A free [NS], block full [2], block free [2],
-    // accumulator full [3][2], drained [3][2] (per accumulator and epilogue group, see search_mma2_kernel), epilogue sync
-    __shared__ uint64_t bars[2 * NP + 2 * NS + 4 + 12 + 1];
+    // packed full [NP], packed free [NP], A full [NS], A free [NS], block full [2][2], block free [2][2],
+    // accumulator full [3][2], drained [3][2] (per accumulator and block, see search_mma2_kernel), epilogue sync [2]
+    __shared__ uint64_t bars[2 * NP + 2 * NS + 8 + 12 + 2];
     __shared__ uint32_t tmem_base_slot;
     __shared__ Watch s_watch;
 
@@ -1280,17 +1302,18 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
         }
         for (int s = 0; s < NS; ++s) {
             mbar_init(bar0 + 8 * (2 * NP + s), TM); // A full
-            mbar_init(bar0 + 8 * (2 * NP + NS + s), 1); // A free
+            mbar_init(bar0 + 8 * (2 * NP + NS + s), 2); // A free: the MMAs of both blocks
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < 4; ++b) {
             mbar_init(bar0 + 8 * (2 * NP + 2 * NS + b), TN); // block full
-            mbar_init(bar0 + 8 * (2 * NP + 2 * NS + 2 + b), 2); // block free: both issuers
+            mbar_init(bar0 + 8 * (2 * NP + 2 * NS + 4 + b), 1); // block free
         }
         for (int a = 0; a < 6; ++a) {
-            mbar_init(bar0 + 8 * (2 * NP + 2 * NS + 4 + a), 1); // accumulator full
-            mbar_init(bar0 + 8 * (2 * NP + 2 * NS + 10 + a), TM); // accumulator drained
+            mbar_init(bar0 + 8 * (2 * NP + 2 * NS + 8 + a), 1); // accumulator full
+            mbar_init(bar0 + 8 * (2 * NP + 2 * NS + 14 + a), TM); // accumulator drained
         }
-        mbar_init(bar0 + 8 * (2 * NP + 2 * NS + 16), 2 * TM); // epilogue sync
+        mbar_init(bar0 + 8 * (2 * NP + 2 * NS + 20), TM); // epilogue sync, block 0
+        mbar_init(bar0 + 8 * (2 * NP + 2 * NS + 21), TM); // block 1
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -1308,26 +1331,24 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
     if (warp == 15) {
         // idle: setmaxnreg works on warpgroups
     } else if (warp == 12 || warp == 13) {
-        // ---- MMA issuers: warp 12 + h issues the tiles with (global tile counter) & 1 == h ----
+        // ---- MMA issuers: warp 12 + h issues every tile against block h (MMA group 2 g + h) ----
         {
             const int h = warp - 12;
             const uint32_t u_tmem = uniform(tmem);
-            const uint64_t desc_b0 = smem_desc(uniform(s_blk));
-            constexpr uint32_t BLOCK_STEP = ATOM_BYTES >> 4;
-            int q = 0;
+            const uint64_t desc_b0 = smem_desc(uniform(s_blk)) + (uint32_t)h * (uint32_t)(ATOM_BYTES >> 4);
+            constexpr uint32_t BUFFER_STEP = (2 * ATOM_BYTES) >> 4;
+            uint32_t s = 0, a_phase = 0;
+            int q = h;
             for (int n = 0; n < nitems; ++n) {
                 const uint32_t b = (uint32_t)n & 1u;
-                if (!mbar_wait(bar_blk_full + 8 * b, ((uint32_t)n >> 1) & 1u, &s_watch))
+                if (!mbar_wait(bar_blk_full + 8 * (2 * b + h), ((uint32_t)n >> 1) & 1u, &s_watch))
                     goto teardown;
-                const uint64_t desc_b = desc_b0 + b * BLOCK_STEP;
-                for (int t = 0; t < ntiles; ++t, ++q) {
-                    if ((q & 1) != h)
-                        continue;
+                const uint64_t desc_b = desc_b0 + b * BUFFER_STEP;
+                for (int t = 0; t < ntiles; ++t, q += 2) {
                     const uint32_t a = (uint32_t)q % 3u;
-                    const uint32_t s = (uint32_t)q % (uint32_t)NS;
-                    if (!mbar_wait(bar_a_full + 8 * s, ((uint32_t)q / (uint32_t)NS) & 1u, &s_watch))
+                    if (!mbar_wait(bar_a_full + 8 * s, a_phase, &s_watch))
                         goto teardown;
-                    if (q >= 3) // the accumulator's previous tile, read by the other epilogue group
+                    if (q >= 3) // the accumulator's previous use, by the other block, has been read
                         if (!mbar_wait(bar_acc_drained + 8 * (2 * a + (1 - h)), (((uint32_t)q - 3u) / 6u) & 1u, &s_watch))
                             goto teardown;
                     tc_fence_after();
@@ -1337,58 +1358,62 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
                             tc_mma_i8_ts(u_tmem + a * TN, u_tmem + V3_A_COL0 + s * 32u + (uint32_t)(kk * 8), desc_b + (uint32_t)((kk * 32) >> 4),
                                          IDESC3, kk != 0);
                         tc_commit(bar_acc_full + 8 * (2 * a + h));
-                        tc_commit(bar_a_free + 8 * s);
+                        tc_commit(bar_a_free + 8 * s); // counts 2: both blocks have read the tile
                     }
                     __syncwarp();
+                    if (++s == NS) {
+                        s = 0;
+                        a_phase ^= 1u;
+                    }
                 }
-                // every MMA this warp issued on the block is complete when this arrives (counts 2: both issuers)
                 if (elect_one())
-                    tc_commit(bar_blk_free + 8 * b);
+                    tc_commit(bar_blk_free + 8 * (2 * b + h)); // every MMA on this block is complete when it arrives
                 __syncwarp();
             }
         }
     } else if (warp == 14) {
-        // ---- loader: per item the packed right block, then the packed left tiles of the row ----
+        // ---- loader: per item the two packed right blocks, then the packed left tiles of the row ----
         if (tid == 14 * 32) {
             int f = 0;
             for (int n = 0; n < nitems; ++n) {
                 const uint32_t* const lrow = p.left + (size_t)row * p.pitch_words;
                 const uint32_t* const rrow = p.right + (size_t)row * p.pitch_words;
-                for (int e = 0; e <= ntiles; ++e, ++f) {
+                for (int e = 0; e < ntiles + 2; ++e, ++f) {
                     const int s = f % NP;
                     if (f >= NP)
                         if (!mbar_wait(bar_packed_free + 8 * s, (f / NP - 1) & 1, &s_watch))
                             goto teardown;
-                    const int base = (e == 0 ? nb : e - 1) * TN;
+                    // a second block beyond the row: one copy of the row's last pixel, which the producers replicate
+                    const int base = e < 2 ? min((2 * bp + e) * TN, cols - 1) : (e - 2) * TN;
                     const uint32_t bytes = (uint32_t)min(TN, cols - base) * 16u;
                     mbar_expect_tx(bar_packed_full + 8 * s, bytes);
-                    bulk_copy_g2s(s_packed + (uint32_t)(s * V3_PACKED_BYTES), (e == 0 ? rrow : lrow) + (size_t)base * 4, bytes, bar_packed_full + 8 * s);
+                    bulk_copy_g2s(s_packed + (uint32_t)(s * V3_PACKED_BYTES), (e < 2 ? rrow : lrow) + (size_t)base * 4, bytes, bar_packed_full + 8 * s);
                 }
-                if (++nb == ntiles) {
-                    nb = 0;
+                if (++bp == npairs) {
+                    bp = 0;
                     ++row;
                 }
             }
         }
     }
     } else if (warp >= 8) {
-        // ---- producers: ring entry 0 of an item = the right block -> shared memory (signed), entries 1.. = left tiles
-        //      -> tensor memory (unsigned). Thread r = row r of the block = TMEM lane r of the tile. ----
+        // ---- producers: ring entries 0, 1 of an item = the right blocks -> shared memory (signed), entries 2.. = left
+        //      tiles -> tensor memory (unsigned). Thread r = row r of a block = TMEM lane r of a tile. ----
         regs_shrink<V3_REGS_PRODUCER>();
         V3_ROLE_CONTEXT
-        const int r = tid - 2 * TM;
+        const int r = (int)pinned((uint32_t)(tid - 2 * TM));
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         int g = 0, q = 0;
         for (int n = 0; n < nitems; ++n) {
-            for (int e = 0; e <= ntiles; ++e, ++g) {
+            for (int e = 0; e < ntiles + 2; ++e, ++g) {
                 const int ps = g % NP;
-                const int base = (e == 0 ? nb : e - 1) * TN;
+                const int base = e < 2 ? min((2 * bp + e) * TN, cols - 1) : (e - 2) * TN;
                 const int valid = min(TN, cols - base);
                 if (!mbar_wait(bar_packed_full + 8 * ps, (g / NP) & 1, &s_watch))
                     goto teardown;
                 const uint4 d = ld_shared_v4(s_packed + (uint32_t)(ps * V3_PACKED_BYTES) + (uint32_t)min(r, valid - 1) * 16u);
-                if (e == 0) {
-                    const uint32_t b = (uint32_t)n & 1u;
+                if (e < 2) {
+                    const uint32_t b = 2u * ((uint32_t)n & 1u) + (uint32_t)e;
                     if (n >= 2) // the MMAs of the item that used this buffer are complete
                         if (!mbar_wait(bar_blk_free + 8 * b, (((uint32_t)n >> 1) - 1u) & 1u, &s_watch))
                             goto teardown;
@@ -1409,72 +1434,81 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
                     ++q;
                 }
             }
-            if (++nb == ntiles) {
-                nb = 0;
+            if (++bp == npairs) {
+                bp = 0;
                 ++row;
             }
         }
     } else {
-        // ---- epilogue: group h = warps 4h..4h+3 takes the tiles with (global tile counter) & 1 == h ----
+        // ---- epilogue: group h = warps 4h..4h+3 owns block h of the item; thread = TMEM lane = left pixel of the tile ----
         regs_grow<V3_REGS_EPILOGUE>();
         V3_ROLE_CONTEXT
-        const int h = warp >> 2;
-        const int lane128 = tid & (TM - 1);
+        const int h = (int)pinned((uint32_t)(warp >> 2));
+        const int lane128 = (int)pinned((uint32_t)(tid & (TM - 1)));
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t my_state = s_state + (uint32_t)(h * V3_STATE_BYTES);
+        const uint32_t my_fin = s_fin + (uint32_t)(h * V3_FIN_BYTES);
+        const uint32_t my_epi = bar_epi + 8u * (uint32_t)h;
         uint32_t R[64];
 #pragma unroll
         for (int c = 0; c < 64; ++c)
             R[c] = 0x7FFF7FFFu;
         uint32_t epi_phase = 0;
-        int q = 0;
+        int q = h;
         for (int n = 0; n < nitems; ++n) {
             const size_t row_at = (size_t)row * cols;
-            for (int t = 0; t < ntiles; ++t, ++q) {
-                if ((q & 1) != h)
-                    continue;
+            const int col0 = (2 * bp + h) * TN; // first right pixel of my block (may lie beyond the row: nothing is stored then)
+            for (int t = 0; t < ntiles; ++t, q += 2) {
                 const int a = q % 3;
                 if (!mbar_wait(bar_acc_full + 8 * (2 * a + h), ((uint32_t)q / 6u) & 1u, &s_watch))
                     goto teardown;
                 tc_fence_after();
-                const uint32_t acc = lane_base + (uint32_t)(a * TN);
-                int va[32], vb[32];
-                tc_load64_packed_issue(acc, va);
-                tc_load64_packed_issue(acc + 64, vb);
-                tc_load32_wait(va);
-                tc_load32_wait(vb);
+                uint32_t v[64];
+                tc_load128_packed(lane_base + (uint32_t)(a * TN), v);
                 tc_fence_before();
                 mbar_arrive(bar_acc_drained + 8 * (2 * a + h));
                 // forward: this left pixel's minimum of 128 ham + column over the block
-                TileMin16 m;
-                fold64_packed<false, 0, true>(va, m);
-                fold64_packed<false, 64, true>(vb, m);
-                const int v = min_of_lanes(m.f);
+                uint32_t f[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    f[c] = __vimin3_s16x2(v[c], v[8 + c], v[16 + c]);
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    f[c] = __vimin3_s16x2(f[c], v[24 + c], v[32 + c]);
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    f[c] = __vimin3_s16x2(f[c], v[40 + c], v[48 + c]);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    f[c] = __vimin3_s16x2(f[c], v[56 + c], f[4 + c]);
+                f[0] = __vimin3_s16x2(f[0], v[60], v[61]);
+                f[1] = __vimin3_s16x2(f[1], v[62], v[63]);
+                const uint32_t m2 = __vimin3_s16x2(f[0], f[1], __vmins2(f[2], f[3]));
+                const int m = min((int)(short)(m2 & 0xFFFFu), (int)(short)(m2 >> 16));
                 const int i = t * TM + lane128;
-                if (i < cols)
-                    atomicMin(p.fwd_first + row_at + i, ((uint32_t)(v >> 7) << 16) | (uint32_t)(nb * TN + (v & 127)));
-                // reverse: per column the minimum of 128 ham + column + tile over the tiles of this group
+                if (i < cols && col0 < cols)
+                    atomicMin(p.fwd_first + row_at + i, ((uint32_t)(m >> 7) << 16) | (uint32_t)(col0 + (m & 127)));
+                // reverse: per column the minimum of 128 ham + column + tile over the tiles
                 const uint32_t tile2 = (uint32_t)t * 0x00010001u;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    R[c] = __viaddmin_s16x2((uint32_t)va[c], tile2, R[c]);
-                    R[32 + c] = __viaddmin_s16x2((uint32_t)vb[c], tile2, R[32 + c]);
-                }
+                for (int c = 0; c < 64; ++c)
+                    R[c] = __viaddmin_s16x2(v[c], tile2, R[c]);
             }
-            // ---- end of the item: the cross-lane reduction of both groups' running minima ----
+            // ---- end of the item: the cross-lane reduction of the running minima ----
             {
-                const uint32_t dst = s_state + (uint32_t)((h * 64 * V3_STATE_STRIDE + lane128) * 4);
+                const uint32_t dst = my_state + (uint32_t)(lane128 * 4);
 #pragma unroll
                 for (int c = 0; c < 64; ++c) {
                     st_shared_u32(dst + (uint32_t)(c * V3_STATE_STRIDE * 4), R[c]);
                     R[c] = 0x7FFF7FFFu;
                 }
-                mbar_arrive(bar_epi);
-                if (!mbar_wait(bar_epi, epi_phase, &s_watch))
+                mbar_arrive(my_epi);
+                if (!mbar_wait(my_epi, epi_phase, &s_watch))
                     goto teardown;
                 epi_phase ^= 1u;
-                // thread = (column pair cp, quarter c4): 64 lanes of one group's row of that pair
-                const int cp = tid & 63, c4 = tid >> 6;
-                const uint32_t src = s_state + (uint32_t)((((c4 >> 1) * 64 + cp) * V3_STATE_STRIDE + (c4 & 1) * 64) * 4);
+                // thread = (column pair cp, half lh of the lanes): 64 lanes of that pair's row
+                const int cp = lane128 & 63, lh = lane128 >> 6;
+                const uint32_t src = my_state + (uint32_t)((cp * V3_STATE_STRIDE + lh * 64) * 4);
                 uint32_t mlo = 0xFFFFFFFFu, mhi = 0xFFFFFFFFu;
 #pragma unroll
                 for (int l4 = 0; l4 < 16; ++l4) {
@@ -1486,24 +1520,23 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
                         mlo = min(mlo, (ww[k] << 16) + (uint32_t)(4 * l4 + k));
                     }
                 }
-                const uint32_t lane0 = (uint32_t)(c4 & 1) * 64u;
-                st_shared_v2(s_fin + (uint32_t)((c4 * TN + 2 * cp) * 4), mlo + lane0, mhi + lane0);
-                mbar_arrive(bar_epi);
-                if (!mbar_wait(bar_epi, epi_phase, &s_watch))
+                const uint32_t lane0 = (uint32_t)lh * 64u;
+                st_shared_v2(my_fin + (uint32_t)((lh * TN + 2 * cp) * 4), mlo + lane0, mhi + lane0);
+                mbar_arrive(my_epi);
+                if (!mbar_wait(my_epi, epi_phase, &s_watch))
                     goto teardown;
                 epi_phase ^= 1u;
-                if (tid < TN) {
-                    const int col = nb * TN + tid;
-                    uint32_t k = min(min(ld_shared_u32(s_fin + (uint32_t)(tid * 4)), ld_shared_u32(s_fin + (uint32_t)((TN + tid) * 4))),
-                                     min(ld_shared_u32(s_fin + (uint32_t)((2 * TN + tid) * 4)), ld_shared_u32(s_fin + (uint32_t)((3 * TN + tid) * 4))));
+                {
+                    const int col = col0 + lane128;
+                    const uint32_t k = min(ld_shared_u32(my_fin + (uint32_t)(lane128 * 4)), ld_shared_u32(my_fin + (uint32_t)((TN + lane128) * 4)));
                     // k = (128 ham + column + tile) << 16 | lane
-                    const uint32_t v = (k >> 16) - (uint32_t)tid;
+                    const uint32_t vv = (k >> 16) - (uint32_t)lane128;
                     if (col < cols)
-                        p.rev_first[row_at + col] = ((v >> 7) << 16) | ((v & 127u) * TM + (k & 0xFFFFu));
+                        p.rev_first[row_at + col] = ((vv >> 7) << 16) | ((vv & 127u) * TM + (k & 0xFFFFu));
                 }
             }
-            if (++nb == ntiles) {
-                nb = 0;
+            if (++bp == npairs) {
+                bp = 0;
                 ++row;
             }
         }
@@ -1606,7 +1639,8 @@ cudaError_t launch_k3(MmaArgs p, cudaStream_t stream) {
     cudaError_t err = configure_once(kernel, V3_SMEM_BYTES);
     if (err != cudaSuccess)
         return err;
-    p.items = (long long)p.rows * p.ntiles; // (row, block of 128 right pixels)
+    p.mtiles = (p.cols + 2 * TN - 1) / (2 * TN); // pairs of right blocks per row
+    p.items = (long long)p.rows * p.mtiles; // (row, pair of blocks of 128 right pixels)
     if (p.items > 0x7FFFFFFFLL)
         return cudaErrorInvalidConfiguration;
     // the forward keys of a row are merged over its blocks with atomicMin

@@ -28,6 +28,7 @@ constexpr int CHAINS = 8;
 #define IMADHI(x, y) asm volatile("mad.hi.u32 %0, %0, %1, %1;" : "+r"(x) : "r"(y))
 #define IMADWIDE(x2, x, y) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x2) : "r"(x), "r"(y))
 #define SHR(x, y) asm volatile("shr.u32 %0, %0, %1;" : "+r"(x) : "r"(y))
+#define HMIN2(x, y) asm volatile("min.f16x2 %0, %0, %1;" : "+r"(x) : "r"(y))
 #define DP4A(x, y) asm volatile("dp4a.u32.u32 %0, %0, %1, %0;" : "+r"(x) : "r"(y))
 
 template<int MODE>
@@ -74,6 +75,13 @@ __global__ void bench(uint32_t* out, long long* cycles, int iters, uint32_t seed
             if (MODE == 27) { SHR(x[c], y); }
             if (MODE == 28) { IMADHI(x[c], y); LOP(x[c], y); }
             if (MODE == 29) { IMADWIDE(x2[c], x[c], y); LOP(x[c], y); }
+            if (MODE == 30) { x[c] = __viaddmin_s16x2(x[c], y, x[(c + 3) % CHAINS]); }   // VIADDMNMX.S16x2: the elementwise fold of search_mma3
+            if (MODE == 31) { x[c] = __vimin3_s16x2(x[c], x[(c + 1) % CHAINS], x[(c + 3) % CHAINS]); } // VIMNMX3.S16x2: the in-thread fold
+            if (MODE == 32) { x[c] = __viaddmin_s16x2(x[c], y, x[(c + 3) % CHAINS]); IMAD(x[c], y); } // + FMA-pipe co-issue
+            if (MODE == 33) { x[c] = __vimin3_s16x2(x[c], x[(c + 1) % CHAINS], x[(c + 3) % CHAINS]); LOP(x[c], y); }
+            if (MODE == 34) { HMIN2(x[c], x[(c + 3) % CHAINS]); }                           // HMNMX2: which pipe?
+            if (MODE == 35) { HMIN2(x[c], x[(c + 3) % CHAINS]); LOP(x[c], y); }
+            if (MODE == 36) { x[c] = __viaddmin_s16x2(x[c], y, x[(c + 3) % CHAINS]); HMIN2(x[(c + 1) % CHAINS], x[(c + 5) % CHAINS]); }
             if (MODE == 15) { POPC(x[c]); POPC(x[c]); POPC(x[c]); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); LOP(x[c], y); MINU(x[c], y); MINU(x[c], y); IMAD(x[c], y); IMAD(x[c], y); IMAD(x[c], y); } // search-like
         }
     }
@@ -180,5 +188,12 @@ int main(int argc, char** argv) {
     run<27>("SHR", 1, sms, out, cyc);
     run<28>("IMAD.HI+LOP3", 2, sms, out, cyc);
     run<29>("IMAD.WIDE+LOP3", 2, sms, out, cyc);
+    run<30>("VIADDMNMX.S16x2", 1, sms, out, cyc);
+    run<31>("VIMNMX3.S16x2", 1, sms, out, cyc);
+    run<32>("VIADDMNMX.S16x2+IMAD", 2, sms, out, cyc);
+    run<33>("VIMNMX3.S16x2+LOP3", 2, sms, out, cyc);
+    run<34>("HMNMX2 (min.f16x2)", 1, sms, out, cyc);
+    run<35>("HMNMX2+LOP3", 2, sms, out, cyc);
+    run<36>("VIADDMNMX.S16x2+HMNMX2", 2, sms, out, cyc);
     return 0;
 }

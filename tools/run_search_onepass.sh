@@ -10,6 +10,7 @@ run 256 4 4 2 0 64 0 2
 run 128 1 4 2 0 64 0 2
 run 1 1 4 2 0 64 0 2
 run 130 3 4 2 1 64 0 2
+run 300 5 4 2 1 64 0 2
 run 1000 8 4 2 1 64 0 2
 run 1280 32 4 2 3 64 0 2
 run 1920 33 4 2 3 8 0 2
@@ -21,4 +22,4 @@ run 2048 1536 4 2 5 64 2 2
 run 1920 1200 4 2 5 64 0 2
 run 1280 1024 4 2 5 64 0 2
 grep -c identical "$out"; grep -c "MISMATCH\|error\|exit [1-9]" "$out"
-cat "$out"
+grep "^cols" "$out" | sed 's/forward ties.*, //'
