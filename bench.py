@@ -511,15 +511,20 @@ def main():
                 "measured POPC issue rate; 3 POPC are issued per 128-bit pair, pipe_frac is the share of the POPC pipe in use",
     }
     int8_peak, int8_src = measure_int8_peak()
-    dirs = 2  # Consistency: forward and reverse search, each a full W x W x 128 product per row
+    # Consistency: the two-pass kernels (mma1 / mma2) compute a full W x W x 128 product per row and direction; the
+    # one-pass kernel (mma3, the default for this workload) takes both directions from ONE product
+    onepass = search_kernel.startswith("mma3")
+    dirs = 1 if onepass else 2
     # SURVEY 8d scores every left/right descriptor pair of a row ONCE, however often an implementation visits it:
     # `frac` is that algorithmic figure, `frac_executed` counts what the kernel issues (both directions)
     mma_ops_once = 2.0 * COLS * px * 32 * K
     mma_ops = mma_ops_once * dirs
-    smem_bytes = (COLS / 128) * (px / 128) * dirs * 26 * 1024  # variant 2, per 128x128 tile: 16 KB operand reads, 8 KB expansion, 2 KB packed ring
+    # shared-memory bytes per 128x128 tile. mma2: 16 KB operand reads, 8 KB expansion, 2 KB packed ring; mma3: 16 KB block
+    # reads (the streamed operand goes to tensor memory), 1 KB packed ring, 2 KB block expansion + reduction per item / 16 tiles
+    smem_bytes = (COLS / 128) * (px / 128) * dirs * (19 if onepass else 26) * 1024
     mma_line = {
         "kernel": search_kernel, "bound": "tensor", "achieved": mma_ops_once / t_mma / 1e12,
-        "peak": int8_peak, "unit": "TOP/s", "frac": mma_ops_once / t_mma / 1e12 / int8_peak, "traffic": traffic.get("search_mma2"),
+        "peak": int8_peak, "unit": "TOP/s", "frac": mma_ops_once / t_mma / 1e12 / int8_peak, "traffic": traffic.get("search_mma3" if onepass else "search_mma2"),
         "peak_kind": "dense int8 tensor rate (tcgen05 kind::i8)", "peak_source": int8_src, "ms_per_launch": t_mma * 1e3,
         "achieved_executed": mma_ops / t_mma / 1e12, "frac_executed": mma_ops / t_mma / 1e12 / int8_peak,
         "executed_over_algorithmic": dirs,
@@ -535,10 +540,11 @@ def main():
                                "frac": popc_alg / t_mma / popc_peak, "peak_source": popc_src},
         "note": "the tensor-core engine (default): W x W x 128-bit Hamming matrix per row as int8 tcgen05.mma (kind::i8, TMEM "
                 "accumulators), argmin in the epilogue. frac = 2*W*P*bits int8 ops (every descriptor pair once, SURVEY 8d) over "
-                "the stage time and the dense int8 rate; frac_executed counts both directions of the consistency check, which "
-                "this kernel computes as two products (column-wise minima of one product cost more instructions than the "
-                "second product: profiles/r02_ncu_search_mma_history.md). smem_frac: shared-memory bytes the kernel moves "
-                "(streamed-operand reads of the MMAs, the resident operand lives in TMEM, + operand expansion) over 128 B/clk/SM",
+                "the stage time and the dense int8 rate; frac_executed counts what the kernel issues: the same for the one-pass "
+                "kernel (mma3: forward minima in-thread, reverse minima elementwise across the row's tiles, both from one "
+                "product), twice that for the two-pass kernels (mma1 / mma2). The one-pass kernel is bound by the ALU pipe "
+                "(the two folds), not by the tensor pipe: profiles/r02_ncu_search_mma_history.md. smem_frac: shared-memory "
+                "bytes the kernel moves over 128 B/clk/SM",
     }
     roofline = mma_line if tensor else popc_line
     roofline["engine"] = "tensor" if tensor else "popc"

@@ -1177,17 +1177,6 @@ __device__ __forceinline__ void tc_store8(uint32_t taddr, const uint32_t (&v)[8]
                  : "memory");
 }
 
-// 128 consecutive accumulator columns of this thread's lane, the low halves of columns 2r and 2r + 1 in register r
-__device__ __forceinline__ void tc_load128_packed(uint32_t taddr, uint32_t (&v)[64]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x64.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
-        : "r"(taddr)
-        : "memory"
-    );
-}
-
 __device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
@@ -1338,6 +1327,9 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
             const uint64_t desc_b0 = smem_desc(uniform(s_blk)) + (uint32_t)h * (uint32_t)(ATOM_BYTES >> 4);
             constexpr uint32_t BUFFER_STEP = (2 * ATOM_BYTES) >> 4;
             uint32_t s = 0, a_phase = 0;
+            // MMA group q = 2 g + h: accumulator a = q % 3; its previous use was group q - 3 of the other block, whose
+            // "drained" barrier completes phase ((q - 3) / 6) & 1: both carried incrementally (d6 = (q - 3) % 6)
+            uint32_t a = (uint32_t)h, d6 = (uint32_t)h + 3u, d_phase = 1u; // q = h: "q - 3 < 0", nothing to wait for until q >= 3
             int q = h;
             for (int n = 0; n < nitems; ++n) {
                 const uint32_t b = (uint32_t)n & 1u;
@@ -1345,11 +1337,10 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
                     goto teardown;
                 const uint64_t desc_b = desc_b0 + b * BUFFER_STEP;
                 for (int t = 0; t < ntiles; ++t, q += 2) {
-                    const uint32_t a = (uint32_t)q % 3u;
                     if (!mbar_wait(bar_a_full + 8 * s, a_phase, &s_watch))
                         goto teardown;
                     if (q >= 3) // the accumulator's previous use, by the other block, has been read
-                        if (!mbar_wait(bar_acc_drained + 8 * (2 * a + (1 - h)), (((uint32_t)q - 3u) / 6u) & 1u, &s_watch))
+                        if (!mbar_wait(bar_acc_drained + 8 * (2 * a + (1 - h)), d_phase, &s_watch))
                             goto teardown;
                     tc_fence_after();
                     if (elect_one()) {
@@ -1364,6 +1355,12 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
                     if (++s == NS) {
                         s = 0;
                         a_phase ^= 1u;
+                    }
+                    a = a == 0 ? 2u : a - 1u; // (a + 2) % 3
+                    d6 += 2u;
+                    if (d6 >= 6u) {
+                        d6 -= 6u;
+                        d_phase ^= 1u;
                     }
                 }
                 if (elect_one())
@@ -1454,45 +1451,71 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
         for (int c = 0; c < 64; ++c)
             R[c] = 0x7FFF7FFFu;
         uint32_t epi_phase = 0;
-        int q = h;
+        // MMA group q = 2 g + h of this block: accumulator q % 3, barrier phase (q / 6) & 1, both carried incrementally.
+        // The accumulator is read in two halves of 64 columns, software-pipelined across tiles so that a TMEM load is
+        // in flight during every fold: [lo(t) arrives] load hi(t) | fold lo(t) | [hi(t) arrives, accumulator handed
+        // back] wait for tile t + 1, load lo(t + 1) | fold hi(t).
+        uint32_t a = (uint32_t)h, q6 = (uint32_t)h, acc_phase = 0;
+        int lo[32], hi[32];
+        int left = nitems * ntiles; // tiles still to load
+        if (left > 0) {
+            if (!mbar_wait(bar_acc_full + 8 * (2 * a + h), acc_phase, &s_watch))
+                goto teardown;
+            tc_fence_after();
+            tc_load64_packed_issue(lane_base + a * TN, lo);
+            --left;
+        }
         for (int n = 0; n < nitems; ++n) {
             const size_t row_at = (size_t)row * cols;
             const int col0 = (2 * bp + h) * TN; // first right pixel of my block (may lie beyond the row: nothing is stored then)
-            for (int t = 0; t < ntiles; ++t, q += 2) {
-                const int a = q % 3;
-                if (!mbar_wait(bar_acc_full + 8 * (2 * a + h), ((uint32_t)q / 6u) & 1u, &s_watch))
-                    goto teardown;
-                tc_fence_after();
-                uint32_t v[64];
-                tc_load128_packed(lane_base + (uint32_t)(a * TN), v);
-                tc_fence_before();
-                mbar_arrive(bar_acc_drained + 8 * (2 * a + h));
-                // forward: this left pixel's minimum of 128 ham + column over the block
+            for (int t = 0; t < ntiles; ++t) {
+                const uint32_t tile2 = (uint32_t)t * 0x00010001u;
                 uint32_t f[8];
+                tc_load32_wait(lo);
+                tc_load64_packed_issue(lane_base + a * TN + 64u, hi);
+                // forward (this left pixel's minimum of 128 ham + column over the block) and reverse (per column the
+                // minimum of 128 ham + column + tile over the tiles), first 64 columns
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
-                    f[c] = __vimin3_s16x2(v[c], v[8 + c], v[16 + c]);
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    f[c] = __vimin3_s16x2(f[c], v[24 + c], v[32 + c]);
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    f[c] = __vimin3_s16x2(f[c], v[40 + c], v[48 + c]);
+                    f[c] = __vimin3_s16x2((uint32_t)lo[c], (uint32_t)lo[8 + c], (uint32_t)lo[16 + c]);
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
-                    f[c] = __vimin3_s16x2(f[c], v[56 + c], f[4 + c]);
-                f[0] = __vimin3_s16x2(f[0], v[60], v[61]);
-                f[1] = __vimin3_s16x2(f[1], v[62], v[63]);
-                const uint32_t m2 = __vimin3_s16x2(f[0], f[1], __vmins2(f[2], f[3]));
+                    f[c] = __vimin3_s16x2(f[c], (uint32_t)lo[24 + 2 * c], (uint32_t)lo[25 + 2 * c]);
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    R[c] = __viaddmin_s16x2((uint32_t)lo[c], tile2, R[c]);
+                tc_load32_wait(hi);
+                tc_fence_before();
+                mbar_arrive(bar_acc_drained + 8 * (2 * a + h));
+                // next tile of this block (the next item's first tile after the last one)
+                a = a == 0 ? 2u : a - 1u; // (a + 2) % 3
+                q6 += 2u;
+                if (q6 >= 6u) {
+                    q6 -= 6u;
+                    acc_phase ^= 1u;
+                }
+                if (left > 0) {
+                    if (!mbar_wait(bar_acc_full + 8 * (2 * a + h), acc_phase, &s_watch))
+                        goto teardown;
+                    tc_fence_after();
+                    tc_load64_packed_issue(lane_base + a * TN, lo);
+                    --left;
+                }
+                // last 64 columns
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    f[c] = __vimin3_s16x2(f[c], (uint32_t)hi[c], (uint32_t)hi[8 + c]);
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    f[c] = __vimin3_s16x2(f[c], (uint32_t)hi[16 + c], (uint32_t)hi[24 + c]);
+                const uint32_t m2 = __vimin3_s16x2(__vimin3_s16x2(f[0], f[1], f[2]), __vimin3_s16x2(f[3], f[4], f[5]), __vmins2(f[6], f[7]));
                 const int m = min((int)(short)(m2 & 0xFFFFu), (int)(short)(m2 >> 16));
                 const int i = t * TM + lane128;
                 if (i < cols && col0 < cols)
                     atomicMin(p.fwd_first + row_at + i, ((uint32_t)(m >> 7) << 16) | (uint32_t)(col0 + (m & 127)));
-                // reverse: per column the minimum of 128 ham + column + tile over the tiles
-                const uint32_t tile2 = (uint32_t)t * 0x00010001u;
 #pragma unroll
-                for (int c = 0; c < 64; ++c)
-                    R[c] = __viaddmin_s16x2(v[c], tile2, R[c]);
+                for (int c = 0; c < 32; ++c)
+                    R[32 + c] = __viaddmin_s16x2((uint32_t)hi[c], tile2, R[32 + c]);
             }
             // ---- end of the item: the cross-lane reduction of the running minima ----
             {
