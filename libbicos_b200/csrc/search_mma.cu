@@ -1240,6 +1240,32 @@ __device__ __forceinline__ void expand_block_pixel(const uint4& d, uint32_t tile
     }
 }
 
+// The per-item cross-lane reduction, one thread's share: 64 lanes of one column pair's row of the dumped state ->
+// the minima of (16-bit running minimum) << 16 | lane for the even (lo half) and the odd column. The odd column's key
+// is one LOP3, (w & mask) | lane with the mask in a register; the even column's one IMAD on the otherwise idle FMA
+// pipe, w * 65536 + lane with the factor in a register (ptxas would turn a literal shift into an ALU instruction).
+template<int L>
+__device__ __forceinline__ uint32_t key_of_hi(uint32_t w, uint32_t mask) {
+    uint32_t k;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(k) : "r"(w), "r"(mask), "n"(L));
+    return k;
+}
+template<int L4>
+struct ReduceLanes {
+    static __device__ __forceinline__ void run(uint32_t src, uint32_t mask, uint32_t shl16, uint32_t& mlo, uint32_t& mhi) {
+        const uint4 w = ld_shared_v4(src + 16u * L4);
+        mhi = min(mhi, min(key_of_hi<4 * L4>(w.x, mask), key_of_hi<4 * L4 + 1>(w.y, mask)));
+        mlo = min(mlo, min(w.x * shl16 + (uint32_t)(4 * L4), w.y * shl16 + (uint32_t)(4 * L4 + 1)));
+        mhi = min(mhi, min(key_of_hi<4 * L4 + 2>(w.z, mask), key_of_hi<4 * L4 + 3>(w.w, mask)));
+        mlo = min(mlo, min(w.z * shl16 + (uint32_t)(4 * L4 + 2), w.w * shl16 + (uint32_t)(4 * L4 + 3)));
+        ReduceLanes<L4 + 1>::run(src, mask, shl16, mlo, mhi);
+    }
+};
+template<>
+struct ReduceLanes<16> {
+    static __device__ __forceinline__ void run(uint32_t, uint32_t, uint32_t, uint32_t&, uint32_t&) {}
+};
+
 #define V3_ROLE_CONTEXT \
     uint32_t fresh; \
     asm volatile("mov.u32 %0, 0;" : "=r"(fresh)); \
@@ -1371,21 +1397,38 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
     } else if (warp == 14) {
         // ---- loader: per item the two packed right blocks, then the packed left tiles of the row ----
         if (tid == 14 * 32) {
-            int f = 0;
+            // ring slot and the parity its "free" barrier completes with are carried incrementally; the first NP
+            // entries find their slots free
+            uint32_t slot = 0, free_phase = 1u;
+            bool wrapped = false;
+            const uint32_t tail_bytes = (uint32_t)(cols - (ntiles - 1) * TN) * 16u; // the row's last (possibly short) tile
+            auto put = [&](const uint32_t* src, uint32_t bytes) -> bool {
+                if (wrapped)
+                    if (!mbar_wait(bar_packed_free + 8 * slot, free_phase, &s_watch))
+                        return false;
+                mbar_expect_tx(bar_packed_full + 8 * slot, bytes);
+                bulk_copy_g2s(s_packed + slot * (uint32_t)V3_PACKED_BYTES, src, bytes, bar_packed_full + 8 * slot);
+                if (++slot == (uint32_t)NP) {
+                    slot = 0;
+                    free_phase ^= 1u;
+                    wrapped = true;
+                }
+                return true;
+            };
             for (int n = 0; n < nitems; ++n) {
                 const uint32_t* const lrow = p.left + (size_t)row * p.pitch_words;
                 const uint32_t* const rrow = p.right + (size_t)row * p.pitch_words;
-                for (int e = 0; e < ntiles + 2; ++e, ++f) {
-                    const int s = f % NP;
-                    if (f >= NP)
-                        if (!mbar_wait(bar_packed_free + 8 * s, (f / NP - 1) & 1, &s_watch))
-                            goto teardown;
+                for (int e = 0; e < 2; ++e) {
                     // a second block beyond the row: one copy of the row's last pixel, which the producers replicate
-                    const int base = e < 2 ? min((2 * bp + e) * TN, cols - 1) : (e - 2) * TN;
-                    const uint32_t bytes = (uint32_t)min(TN, cols - base) * 16u;
-                    mbar_expect_tx(bar_packed_full + 8 * s, bytes);
-                    bulk_copy_g2s(s_packed + (uint32_t)(s * V3_PACKED_BYTES), (e < 2 ? rrow : lrow) + (size_t)base * 4, bytes, bar_packed_full + 8 * s);
+                    const int base = min((2 * bp + e) * TN, cols - 1);
+                    if (!put(rrow + (size_t)base * 4, (uint32_t)min(TN, cols - base) * 16u))
+                        goto teardown;
                 }
+                for (int t = 0; t < ntiles - 1; ++t)
+                    if (!put(lrow + (size_t)t * (TN * 4), (uint32_t)V3_PACKED_BYTES))
+                        goto teardown;
+                if (!put(lrow + (size_t)(ntiles - 1) * (TN * 4), tail_bytes))
+                    goto teardown;
                 if (++bp == npairs) {
                     bp = 0;
                     ++row;
@@ -1400,35 +1443,50 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
         V3_ROLE_CONTEXT
         const int r = (int)pinned((uint32_t)(tid - 2 * TM));
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        int g = 0, q = 0;
+        // everything a ring entry needs is carried incrementally: packed slot + parity, A slot + parity
+        uint32_t ps = 0, full_phase = 0, as = 0, a_free_phase = 1u;
+        bool a_wrapped = false;
+        const uint32_t my_px = s_packed + (uint32_t)r * 16u; // this thread's pixel of a full tile, + slot * V3_PACKED_BYTES
+        const uint32_t my_tail_px = s_packed + (uint32_t)min(r, cols - (ntiles - 1) * TN - 1) * 16u; // of the row's last tile
         for (int n = 0; n < nitems; ++n) {
-            for (int e = 0; e < ntiles + 2; ++e, ++g) {
-                const int ps = g % NP;
-                const int base = e < 2 ? min((2 * bp + e) * TN, cols - 1) : (e - 2) * TN;
-                const int valid = min(TN, cols - base);
-                if (!mbar_wait(bar_packed_full + 8 * ps, (g / NP) & 1, &s_watch))
+            for (int e = 0; e < 2; ++e) {
+                const int valid = min(TN, cols - min((2 * bp + e) * TN, cols - 1));
+                if (!mbar_wait(bar_packed_full + 8 * ps, full_phase, &s_watch))
                     goto teardown;
-                const uint4 d = ld_shared_v4(s_packed + (uint32_t)(ps * V3_PACKED_BYTES) + (uint32_t)min(r, valid - 1) * 16u);
-                if (e < 2) {
-                    const uint32_t b = 2u * ((uint32_t)n & 1u) + (uint32_t)e;
-                    if (n >= 2) // the MMAs of the item that used this buffer are complete
-                        if (!mbar_wait(bar_blk_free + 8 * b, (((uint32_t)n >> 1) - 1u) & 1u, &s_watch))
-                            goto teardown;
-                    expand_block_pixel(d, s_blk + b * ATOM_BYTES, r);
-                    mbar_arrive(bar_packed_free + 8 * ps); // after the stores that consumed the loaded registers
-                    fence_async_smem();
-                    mbar_arrive(bar_blk_full + 8 * b);
-                } else {
-                    const uint32_t s = (uint32_t)q % (uint32_t)NS;
-                    if (q >= NS)
-                        if (!mbar_wait(bar_a_free + 8 * s, ((uint32_t)q / (uint32_t)NS - 1u) & 1u, &s_watch))
-                            goto teardown;
-                    tc_fence_after();
-                    expand_moving_to_tmem(d, lane_base + V3_A_COL0 + s * 32u);
-                    mbar_arrive(bar_packed_free + 8 * ps);
-                    tc_fence_before();
-                    mbar_arrive(bar_a_full + 8 * s);
-                    ++q;
+                const uint4 d = ld_shared_v4(s_packed + ps * (uint32_t)V3_PACKED_BYTES + (uint32_t)min(r, valid - 1) * 16u);
+                const uint32_t b = 2u * ((uint32_t)n & 1u) + (uint32_t)e;
+                if (n >= 2) // the MMAs of the item that used this buffer are complete
+                    if (!mbar_wait(bar_blk_free + 8 * b, (((uint32_t)n >> 1) - 1u) & 1u, &s_watch))
+                        goto teardown;
+                expand_block_pixel(d, s_blk + b * ATOM_BYTES, r);
+                mbar_arrive(bar_packed_free + 8 * ps); // after the stores that consumed the loaded registers
+                fence_async_smem();
+                mbar_arrive(bar_blk_full + 8 * b);
+                if (++ps == (uint32_t)NP) {
+                    ps = 0;
+                    full_phase ^= 1u;
+                }
+            }
+            for (int t = 0; t < ntiles; ++t) {
+                if (!mbar_wait(bar_packed_full + 8 * ps, full_phase, &s_watch))
+                    goto teardown;
+                const uint4 d = ld_shared_v4((t == ntiles - 1 ? my_tail_px : my_px) + ps * (uint32_t)V3_PACKED_BYTES);
+                if (a_wrapped)
+                    if (!mbar_wait(bar_a_free + 8 * as, a_free_phase, &s_watch))
+                        goto teardown;
+                tc_fence_after();
+                expand_moving_to_tmem(d, lane_base + V3_A_COL0 + as * 32u);
+                mbar_arrive(bar_packed_free + 8 * ps);
+                tc_fence_before();
+                mbar_arrive(bar_a_full + 8 * as);
+                if (++ps == (uint32_t)NP) {
+                    ps = 0;
+                    full_phase ^= 1u;
+                }
+                if (++as == (uint32_t)NS) {
+                    as = 0;
+                    a_free_phase ^= 1u;
+                    a_wrapped = true;
                 }
             }
             if (++bp == npairs) {
@@ -1455,7 +1513,7 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
         // The accumulator is read in two halves of 64 columns, software-pipelined across tiles so that a TMEM load is
         // in flight during every fold: [lo(t) arrives] load hi(t) | fold lo(t) | [hi(t) arrives, accumulator handed
         // back] wait for tile t + 1, load lo(t + 1) | fold hi(t).
-        uint32_t a = (uint32_t)h, q6 = (uint32_t)h, acc_phase = 0;
+        uint32_t a = (uint32_t)h, acc_phase = 0;
         int lo[32], hi[32];
         int left = nitems * ntiles; // tiles still to load
         if (left > 0) {
@@ -1468,6 +1526,7 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
         for (int n = 0; n < nitems; ++n) {
             const size_t row_at = (size_t)row * cols;
             const int col0 = (2 * bp + h) * TN; // first right pixel of my block (may lie beyond the row: nothing is stored then)
+            const int fwd_cols = col0 < cols ? cols : 0; // left pixels whose forward key this block may lower
             for (int t = 0; t < ntiles; ++t) {
                 const uint32_t tile2 = (uint32_t)t * 0x00010001u;
                 uint32_t f[8];
@@ -1489,11 +1548,8 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
                 mbar_arrive(bar_acc_drained + 8 * (2 * a + h));
                 // next tile of this block (the next item's first tile after the last one)
                 a = a == 0 ? 2u : a - 1u; // (a + 2) % 3
-                q6 += 2u;
-                if (q6 >= 6u) {
-                    q6 -= 6u;
+                if (a == (uint32_t)h) // q = 2 g + h passes a multiple of 6 exactly when its accumulator index returns to h
                     acc_phase ^= 1u;
-                }
                 if (left > 0) {
                     if (!mbar_wait(bar_acc_full + 8 * (2 * a + h), acc_phase, &s_watch))
                         goto teardown;
@@ -1509,10 +1565,11 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
                 for (int c = 0; c < 8; ++c)
                     f[c] = __vimin3_s16x2(f[c], (uint32_t)hi[16 + c], (uint32_t)hi[24 + c]);
                 const uint32_t m2 = __vimin3_s16x2(__vimin3_s16x2(f[0], f[1], f[2]), __vimin3_s16x2(f[3], f[4], f[5]), __vmins2(f[6], f[7]));
-                const int m = min((int)(short)(m2 & 0xFFFFu), (int)(short)(m2 >> 16));
+                // both halves are non-negative: m = 128 ham + column; key = ham << 16 | col0 + column = 512 m - 511 (m & 127) + col0
+                const uint32_t m = min(m2 & 0xFFFFu, m2 >> 16);
                 const int i = t * TM + lane128;
-                if (i < cols && col0 < cols)
-                    atomicMin(p.fwd_first + row_at + i, ((uint32_t)(m >> 7) << 16) | (uint32_t)(col0 + (m & 127)));
+                if (i < fwd_cols)
+                    atomicMin(p.fwd_first + row_at + i, m * 512u + (uint32_t)col0 - (m & 127u) * 511u);
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
                     R[32 + c] = __viaddmin_s16x2((uint32_t)hi[c], tile2, R[32 + c]);
@@ -1533,16 +1590,7 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
                 const int cp = lane128 & 63, lh = lane128 >> 6;
                 const uint32_t src = my_state + (uint32_t)((cp * V3_STATE_STRIDE + lh * 64) * 4);
                 uint32_t mlo = 0xFFFFFFFFu, mhi = 0xFFFFFFFFu;
-#pragma unroll
-                for (int l4 = 0; l4 < 16; ++l4) {
-                    const uint4 w = ld_shared_v4(src + 16u * l4);
-                    const uint32_t ww[4] = { w.x, w.y, w.z, w.w };
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        mhi = min(mhi, (ww[k] & 0xFFFF0000u) + (uint32_t)(4 * l4 + k));
-                        mlo = min(mlo, (ww[k] << 16) + (uint32_t)(4 * l4 + k));
-                    }
-                }
+                ReduceLanes<0>::run(src, pinned(0xFFFF0000u), pinned(65536u), mlo, mhi);
                 const uint32_t lane0 = (uint32_t)lh * 64u;
                 st_shared_v2(my_fin + (uint32_t)((lh * TN + 2 * cp) * 4), mlo + lane0, mhi + lane0);
                 mbar_arrive(my_epi);
