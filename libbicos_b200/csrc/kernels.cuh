@@ -131,6 +131,7 @@ cudaError_t launch_search_mma(
 bool search_mma_colterm(); // see search_mma.cu, fold32
 void set_search_mma_colterm(bool on);
 bool search_mma_supports(int K, int cols);
+bool search_mma_onepass_applies(int K, int cols, int flags, int free_top_bits); // would launch_search_mma take search_mma3_kernel?
 int search_mma_smem_bytes(int K);
 int search_mma_variant(); // tensor-core kernel variant, see search_mma.cu
 void set_search_mma_variant(int v);

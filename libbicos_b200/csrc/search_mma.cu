@@ -1822,6 +1822,13 @@ void set_search_mma_colterm(bool on) {
     g_colterm.store(on ? 1 : 0, std::memory_order_relaxed);
 }
 
+// Whether launch_search_mma takes the one-pass consistency kernel (search_mma3_kernel) for this search
+bool search_mma_onepass_applies(int K, int cols, int flags, int free_top_bits) {
+    const int variant = search_mma_variant();
+    return K == 4 && cols >= 1 && cols <= COL_MAX + 1 && flags == FLAG_CONSISTENCY && free_top_bits >= 2 && (variant == 3 || variant == 0)
+        && search_mma_colterm();
+}
+
 bool search_mma_supports(int K, int cols) {
     return (K == 4 || K == 8 || K == 12 || K == 16) && cols >= 1 && cols <= COL_MAX + 1;
 }
@@ -1865,7 +1872,7 @@ cudaError_t launch_search_mma(
     const long long pair_items = (long long)dirs * rows * ((cols + 2 * TM - 1) / (2 * TM));
     const int variant = search_mma_variant();
     // one product for both directions: 128-bit descriptors whose top TWO bits are free, Consistency without no_dupes
-    if (K == 4 && flags == FLAG_CONSISTENCY && free_top_bits >= 2 && (variant == 3 || variant == 0) && search_mma_colterm()) {
+    if (search_mma_onepass_applies(K, cols, flags, free_top_bits)) {
         note_search_kernel("mma3<K=4,nodupes=0,ct=2,onepass=1>");
         return launch_k3(p, stream);
     }
