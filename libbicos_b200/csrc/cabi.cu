@@ -303,11 +303,7 @@ struct bicos_b200_handle_s {
     cudaEvent_t ev_in[MAX_BANDS] = {}, ev_done[MAX_BANDS] = {};
     // two-stream pipeline of bicos_b200_match_batch: transform + search of unit u + 1 beside the refine of unit u
     DeviceBuffer keys_b; // second set of key arrays (unit parity)
-    DeviceBuffer compact; // subpixel refine: per-row lists of the pixels that passed the postfilter + the row counters
     bool overlap = true; // bicos_b200_set_overlap
-    // subpixel refine as postfilter + compaction + refinement over full warps (environment BICOS_B200_COMPACT_REFINE=0: the
-    // one-kernel form, for A/B timing)
-    bool compact_refine = [] { const char* v = getenv("BICOS_B200_COMPACT_REFINE"); return !(v && v[0] == '0'); }();
     cudaStream_t p_search = nullptr, p_refine = nullptr;
     cudaEvent_t p_start = nullptr, p_done = nullptr, p_searched[2] = {}, p_refined[2] = {};
     // optional per-stage timing (bicos_b200_set_profiling)
@@ -502,16 +498,6 @@ int do_refine(
     prm.disp_pitch = disparity_pitch;
     prm.corr_out = prm.has_threshold ? corrmap : nullptr;
     prm.corr_pitch = corrmap_pitch;
-    prm.compact_list = nullptr;
-    prm.compact_counts = nullptr;
-    if (prm.subpixel && h->compact_refine) {
-        // postfilter + compaction as a kernel of its own, the refinement over full warps (refine.cu, COMPACT)
-        const size_t list_bytes = (size_t)rows * cols * sizeof(uint32_t);
-        CU(h->compact.reserve(list_bytes + (size_t)rows * sizeof(unsigned int)));
-        prm.compact_list = static_cast<uint32_t*>(h->compact.ptr);
-        prm.compact_counts = reinterpret_cast<unsigned int*>(static_cast<char*>(h->compact.ptr) + list_bytes);
-        h->launches += 1;
-    }
     CU(launch_refine(t0, t1, prm, stream));
     h->launches += 1;
     return 0;
@@ -772,7 +758,6 @@ int bicos_b200_destroy(bicos_b200_handle h) {
         if (h->ev_last)
             cudaEventDestroy(h->ev_last);
         h->keys_b.release();
-        h->compact.release();
         for (cudaEvent_t e: { h->p_start, h->p_done, h->p_searched[0], h->p_searched[1], h->p_refined[0], h->p_refined[1] })
             if (e)
                 cudaEventDestroy(e);

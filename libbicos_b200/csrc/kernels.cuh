@@ -55,11 +55,6 @@ struct RefineParams {
     size_t disp_pitch; // bytes
     void* corr_out; // float32 or float64, may be null
     size_t corr_pitch; // bytes
-    // subpixel mode, optional workspace: [rows][cols] uint32 + [rows] counters. With both set the postfilter runs as
-    // a kernel of its own that lists the pixels with a candidate per row, and the refinement runs over the lists
-    // (full warps); without them the one-kernel form runs.
-    uint32_t* compact_list;
-    unsigned int* compact_counts;
 };
 
 // kernel 1: temporal descriptor transform (reference a2/a3/a4)
