@@ -22,9 +22,10 @@
 // tcgen05.ld packs the low halves of two accumulator columns into one register and one
 // VIADDMNMX.S16x2 folds two pairs (the popcount engine needs 3 POPC + 6 LOP3 + 5 more per pair);
 // wider descriptors use the 32-bit VIADDMNMX, one pair per instruction.
-// The reverse search of the consistency check (bicos.hpp:99-106) is the same kernel with the
-// operands swapped (the second half of the work items): on the tensor cores the second
-// W x W x KBITS product is cheaper than column-wise minima of the first.
+// The reverse search of the consistency check (bicos.hpp:99-106) is, in the first two kernels, the same
+// kernel with the operands swapped (the second half of the work items): on the tensor cores the second
+// W x W x KBITS product is cheaper than column-wise minima of the first TAKEN PER TILE; the third kernel
+// takes them per item instead and computes the product once.
 //
 // Persistent CTAs walk contiguous ranges of work items (direction, row, M tile); within a CTA four
 // roles are hand-shaken by mbarriers only:
@@ -37,10 +38,12 @@
 //              (128 x 128 x 32, kind::i8) per tile and the commits to the stage / accumulator barriers
 //   epilogue   4 warps per 128 left pixels (the four TMEM lane quadrants): tcgen05.ld the accumulator,
 //              hand it back, fold it into the running minima; expand the next item's left tile in passing
-// Two kernels: search_mma_kernel (every width; 2 CTAs per SM up to 256 bits; 128 left pixels per item,
-// both operands in shared memory, 2 accumulators) and search_mma2_kernel (128 / 256 bits, large images;
+// Three kernels: search_mma_kernel (every width; 2 CTAs per SM up to 256 bits; 128 left pixels per item,
+// both operands in shared memory, 2 accumulators), search_mma2_kernel (128 / 256 bits, large images;
 // 1 CTA per SM, 256 left pixels per item, left operand resident in TMEM, 3 accumulators in rotation,
-// one issuer per half). DESIGN.md 3.2a has the measurements that led from one to the other.
+// one issuer per half) and search_mma3_kernel (128 bits, Consistency without no_dupes: ONE product per
+// row, the forward minima folded in-thread and the reverse minima elementwise across the row's tiles,
+// see its own header below). DESIGN.md 3.2a / 3.2b have the measurements that led from one to the next.
 
 #include "kernels.cuh"
 
