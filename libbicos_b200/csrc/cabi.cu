@@ -482,6 +482,7 @@ int do_refine(
     prm.nsteps = 0;
     prm.xs = nullptr;
     prm.one = 1.0f;
+    prm.inv_n = 1.0f / (float)n; // IEEE single-precision division on the host: RN(1 / n)
     if (prm.subpixel) {
         if (int rc = prepare_steps(h, cfg->subpixel_step, stream))
             return rc;

@@ -45,6 +45,7 @@ struct RefineParams {
     int nsteps; // number of x values of the float loop x=-1; x<=1; x+=step
     const float* xs; // device array [nsteps] with exactly those float values
     float one; // 1.0f, passed at run time so that ptxas cannot fold x * one (refine.cu, fma2 note)
+    float inv_n; // RN(1 / n) in float: the float means are sum / n as three FMA-pipe operations (refine.cu, mean_of_sum)
     int nodupes_forward; // forward search must be unique: compare fwd_first with fwd_last
     const uint32_t* fwd_first;
     const uint32_t* fwd_last;

@@ -199,3 +199,30 @@ def test_synth_is_shardable_and_backend_independent():
         assert np.array_equal(a[0], b[0].view(torch.int16).numpy().view(np.uint16) if dt == np.uint16 else b[0].numpy())
         assert np.array_equal(a[2], b[2].numpy())
     assert zlib.crc32(full[0].tobytes()) != zlib.crc32(synth.make_stacks(5, 64, 48, np.uint8, seed=3, frame=1)[0].tobytes())
+
+
+def test_mean_by_reciprocal_is_the_ieee_quotient():
+    """refine.cu computes the float means sum / n as q0 = RN(s r), rem = s - q0 n (one FMA, exact), q = RN(q0 + rem r)
+    with r = RN(1 / n) (mean_of_sum) instead of an IEEE division (reference include/impl/cpu/agree.hpp:34-36, cv::mean
+    in float): the same float for EVERY integer sum in [0, 65535 n] and every stack size 2 <= n <= 65. Emulated in
+    float64, where every intermediate is exact except the last sum; results whose float64 value lies within one
+    float64 ulp of a float32 rounding midpoint (where that emulation could round twice) are re-checked in rationals."""
+    from fractions import Fraction
+
+    f32 = np.float32
+    flagged = 0
+    for n in range(2, 66):
+        a = np.arange(0, n * 65535 + 1, dtype=np.float64)
+        r = np.float64(f32(1.0) / f32(n))
+        want = (a.astype(f32) / f32(n)).astype(np.float64)
+        q0 = (a * r).astype(f32).astype(np.float64)  # 24 x 24 bits: exact in float64, then RN to float32
+        rem = (a - q0 * n).astype(f32).astype(np.float64)  # the FMA's exact value (q0 n: 31 bits; the difference is small)
+        t = q0 + rem * r  # rem r exact (48 bits); the sum may round in float64
+        assert np.array_equal(t.astype(f32).astype(np.float64), want), n
+        low = t.view(np.int64) & ((1 << 29) - 1)  # float64 mantissa bits below float32 precision
+        for i in np.nonzero(np.abs(low - (1 << 28)) <= 1)[0]:
+            flagged += 1
+            exact = Fraction(float(q0[i])) + Fraction(float(rem[i])) * Fraction(float(r))
+            lo, hi = f32(np.nextafter(f32(want[i]), f32(-np.inf))), f32(np.nextafter(f32(want[i]), f32(np.inf)))
+            assert abs(exact - Fraction(float(want[i]))) <= min(abs(exact - Fraction(float(lo))), abs(exact - Fraction(float(hi))))
+    assert flagged == 0  # none today; the branch above stays for other float environments
