@@ -52,7 +52,7 @@ typedef enum {
  * as bicos_b200_match does; a set top bit with this flag gives wrong matches. */
 #define BICOS_B200_FLAG_TOP_BIT_FREE 4
 /* bicos_b200_search only: bits 32 K - 1 AND 32 K - 2 of every descriptor are zero (also true for everything
- * bicos_b200_transform writes: 4n-6 <= 32K-2, and n^2-2n+3 mod 32 <= 27). With 128-bit descriptors and
+ * bicos_b200_transform writes: 4n-6 <= 32K-2, and n^2-2n+3 mod 32 <= 27). With 128- or 256-bit descriptors and
  * flags = CONSISTENCY the tensor-core engine then takes both directions from ONE product (search_mma.cu,
  * search_mma3_kernel), as bicos_b200_match does. Implies TOP_BIT_FREE. */
 #define BICOS_B200_FLAG_TOP2_BITS_FREE 8

@@ -1157,20 +1157,35 @@ teardown:
 //   warps 8-11       producers      warps 12, 13  MMA issuers (block 0 / 1)      warp 14  loader      warp 15  idle
 // TMEM: three 128-column accumulators in rotation (columns 0..383, MMA group 2 g + h -> accumulator (2 g + h) % 3
 // as in search_mma2_kernel), four A tiles of 32 columns (384..511).
+// 256-bit descriptors (K = 8) run the same kernel: two 128-bit atoms per operand, two A tiles of 64 TMEM columns, and,
+// because popc(right descriptor) no longer fits the signed operand byte, that byte carries popc - 128 and the
+// accumulator is 128 ham + column - 16384 (still a 16-bit value: ham <= 254); the reverse fold adds the 16384 back
+// together with the tile index, the forward fold's minimum adds it when the key is built.
 constexpr int V3_THREADS = 512;
-constexpr int V3_REGS_LAUNCH = 104;
+template<int K>
+constexpr int V3_REGS_LAUNCH = K == 4 ? 104 : 112;
 constexpr int V3_REGS_EPILOGUE = 168; // 64 running minima + 64 accumulator registers
-constexpr int V3_REGS_PRODUCER = 40;
-constexpr int V3_REGS_ISSUER = 40;
-static_assert(256 * V3_REGS_EPILOGUE + 128 * V3_REGS_PRODUCER + 128 * V3_REGS_ISSUER <= V3_THREADS * V3_REGS_LAUNCH, "register budget");
-constexpr int V3_ASLOTS = 4;
+template<int K>
+constexpr int V3_REGS_PRODUCER = K == 4 ? 40 : 56;
+template<int K>
+constexpr int V3_REGS_ISSUER = K == 4 ? 40 : 56;
+template<int K>
+constexpr bool V3_REGS_FIT = 256 * V3_REGS_EPILOGUE + 128 * V3_REGS_PRODUCER<K> + 128 * V3_REGS_ISSUER<K> <= V3_THREADS * V3_REGS_LAUNCH<K>;
+static_assert(V3_REGS_FIT<4> && V3_REGS_FIT<8>, "register budget");
+template<int K>
+constexpr int V3_ASLOTS = K == 4 ? 4 : 2; // A tiles in tensor memory: 128 columns beside the three accumulators
 constexpr int V3_PACKED = 4;
 constexpr uint32_t V3_A_COL0 = 3 * TN;
-constexpr int V3_PACKED_BYTES = TN * 16;
+template<int K>
+constexpr int V3_PACKED_BYTES = TN * K * 4;
+template<int K>
+constexpr int V3_OFFSET = K == 4 ? 0 : 16384; // 128 x the bias of the popcount byte
 constexpr int V3_STATE_STRIDE = 132; // words per column-pair row of 128 lanes: conflict-free LDS.128
 constexpr int V3_STATE_BYTES = 64 * V3_STATE_STRIDE * 4; // per epilogue group
 constexpr int V3_FIN_BYTES = 2 * TN * 4; // per epilogue group
-constexpr int V3_SMEM_BYTES = 4 * ATOM_BYTES + V3_PACKED * V3_PACKED_BYTES + 2 * V3_STATE_BYTES + 2 * V3_FIN_BYTES + 1024;
+template<int K>
+constexpr int V3_SMEM_BYTES = 4 * (K / 4) * ATOM_BYTES + V3_PACKED * V3_PACKED_BYTES<K> + 2 * V3_STATE_BYTES + 2 * V3_FIN_BYTES + 1024;
+static_assert(V3_SMEM_BYTES<8> <= 227 * 1024, "shared memory");
 // instruction descriptor: D = s32, A = unsigned int8 (the streamed left tile), B = signed int8 (the block)
 constexpr uint32_t IDESC3 = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
@@ -1200,8 +1215,11 @@ __device__ __forceinline__ uint32_t pinned(uint32_t v) {
 
 // One left pixel -> its TMEM lane of A slot `taddr`: b * 2^s bytes, TMEM column 8 wi + s = bytes of bits s, 8 + s,
 // 16 + s, 24 + s of word wi. The bytes of the two unused top bits (word 3, byte 3, s = 6 / 7) are 128 and 1.
-__device__ __forceinline__ void expand_moving_to_tmem(const uint4& d, uint32_t taddr) {
-    const uint32_t w[4] = { d.x, d.y, d.z, d.w };
+template<int K>
+__device__ __forceinline__ void expand_moving_to_tmem(const uint4 (&d)[K / 4], uint32_t taddr) {
+#pragma unroll
+    for (int q = 0; q < K / 4; ++q) {
+    const uint32_t w[4] = { d[q].x, d[q].y, d[q].z, d[q].w };
 #pragma unroll
     for (int wi = 0; wi < 4; ++wi) {
         uint32_t v[8];
@@ -1213,11 +1231,12 @@ __device__ __forceinline__ void expand_moving_to_tmem(const uint4& d, uint32_t t
         v[5] = expand_word<true, 5>(w[wi]);
         v[6] = expand_word<true, 6>(w[wi]);
         v[7] = expand_word<true, 7>(w[wi]);
-        if (wi == 3) {
+        if (q == K / 4 - 1 && wi == 3) {
             v[6] |= 128u << 24;
             v[7] |= 1u << 24;
         }
-        tc_store8(taddr + 8u * wi, v);
+        tc_store8(taddr + 32u * q + 8u * wi, v);
+    }
     }
     tc_store_wait();
 }
@@ -1225,21 +1244,31 @@ __device__ __forceinline__ void expand_moving_to_tmem(const uint4& d, uint32_t t
 // One right pixel -> row r of the block tile in shared memory: (1 - 2b) * 2^(7 - s) bytes (128B-swizzled K-major, as
 // expand_pixel). The bytes of the two unused top bits carry popc(descriptor) (against the 128 of the left operand)
 // and the block column r (against the 1).
-__device__ __forceinline__ void expand_block_pixel(const uint4& d, uint32_t tile, int r) {
+template<int K>
+__device__ __forceinline__ void expand_block_pixel(const uint4 (&d)[K / 4], uint32_t tile, int r) {
     const uint32_t row = tile + (uint32_t)r * 128u;
     const uint32_t sw = (uint32_t)(r & 7);
-    const uint32_t w[4] = { d.x, d.y, d.z, d.w };
-    const uint32_t pc = (uint32_t)(__popc(d.x) + __popc(d.y) + __popc(d.z) + __popc(d.w));
+    int pc = 0;
 #pragma unroll
-    for (int wi = 0; wi < 4; ++wi) {
-        st_shared_v4(row + ((((uint32_t)(2 * wi)) ^ sw) << 4), expand_word<false, 0>(w[wi]), expand_word<false, 1>(w[wi]),
-                     expand_word<false, 2>(w[wi]), expand_word<false, 3>(w[wi]));
-        uint32_t s6 = expand_word<false, 6>(w[wi]), s7 = expand_word<false, 7>(w[wi]);
-        if (wi == 3) {
-            s6 = (s6 & 0x00FFFFFFu) | (pc << 24);
-            s7 = (s7 & 0x00FFFFFFu) | ((uint32_t)r << 24);
+    for (int q = 0; q < K / 4; ++q)
+        pc += __popc(d[q].x) + __popc(d[q].y) + __popc(d[q].z) + __popc(d[q].w);
+    // 256 bits: up to 254 set bits, so the signed byte carries popc - 128 (see V3_OFFSET)
+    const uint32_t pc_byte = (uint32_t)(pc - (K == 4 ? 0 : 128)) & 0xFFu;
+#pragma unroll
+    for (int q = 0; q < K / 4; ++q) {
+        const uint32_t w[4] = { d[q].x, d[q].y, d[q].z, d[q].w };
+        const uint32_t atom = row + (uint32_t)q * ATOM_BYTES;
+#pragma unroll
+        for (int wi = 0; wi < 4; ++wi) {
+            st_shared_v4(atom + ((((uint32_t)(2 * wi)) ^ sw) << 4), expand_word<false, 0>(w[wi]), expand_word<false, 1>(w[wi]),
+                         expand_word<false, 2>(w[wi]), expand_word<false, 3>(w[wi]));
+            uint32_t s6 = expand_word<false, 6>(w[wi]), s7 = expand_word<false, 7>(w[wi]);
+            if (q == K / 4 - 1 && wi == 3) {
+                s6 = (s6 & 0x00FFFFFFu) | (pc_byte << 24);
+                s7 = (s7 & 0x00FFFFFFu) | ((uint32_t)r << 24);
+            }
+            st_shared_v4(atom + ((((uint32_t)(2 * wi + 1)) ^ sw) << 4), expand_word<false, 4>(w[wi]), expand_word<false, 5>(w[wi]), s6, s7);
         }
-        st_shared_v4(row + ((((uint32_t)(2 * wi + 1)) ^ sw) << 4), expand_word<false, 4>(w[wi]), expand_word<false, 5>(w[wi]), s6, s7);
     }
 }
 
@@ -1278,15 +1307,15 @@ struct ReduceLanes<16> {
     const int npairs = p.mtiles; /* pairs of right blocks per row */ \
     const long long item0 = p.items * (blockIdx.x + fresh) / gridDim.x; \
     const int nitems = (int)(p.items * (blockIdx.x + fresh + 1) / gridDim.x - item0); \
-    const uint32_t s_blk = ((smem_u32(smem_raw) + fresh) + 1023u) & ~1023u; /* + (2 buffer + block) * ATOM_BYTES */ \
-    const uint32_t s_packed = s_blk + 4 * ATOM_BYTES; \
-    const uint32_t s_state = s_packed + V3_PACKED * V3_PACKED_BYTES; /* + group * V3_STATE_BYTES */ \
+    const uint32_t s_blk = ((smem_u32(smem_raw) + fresh) + 1023u) & ~1023u; /* + (2 buffer + block) * BLK_BYTES */ \
+    const uint32_t s_packed = s_blk + 4 * BLK_BYTES; \
+    const uint32_t s_state = s_packed + NP * PACKED_BYTES; /* + group * V3_STATE_BYTES */ \
     const uint32_t s_fin = s_state + 2 * V3_STATE_BYTES; /* + group * V3_FIN_BYTES */ \
     const uint32_t bar_packed_full = smem_u32(&bars[0]) + fresh; \
-    const uint32_t bar_packed_free = bar_packed_full + 8 * V3_PACKED; \
-    const uint32_t bar_a_full = bar_packed_free + 8 * V3_PACKED; \
-    const uint32_t bar_a_free = bar_a_full + 8 * V3_ASLOTS; \
-    const uint32_t bar_blk_full = bar_a_free + 8 * V3_ASLOTS; /* + 8 * (2 buffer + block) */ \
+    const uint32_t bar_packed_free = bar_packed_full + 8 * NP; \
+    const uint32_t bar_a_full = bar_packed_free + 8 * NP; \
+    const uint32_t bar_a_free = bar_a_full + 8 * NS; \
+    const uint32_t bar_blk_full = bar_a_free + 8 * NS; /* + 8 * (2 buffer + block) */ \
     const uint32_t bar_blk_free = bar_blk_full + 32; \
     const uint32_t bar_acc_full = bar_blk_free + 32; \
     const uint32_t bar_acc_drained = bar_acc_full + 48; \
@@ -1296,9 +1325,15 @@ struct ReduceLanes<16> {
         (void)bar_a_full, (void)bar_a_free, (void)bar_blk_full, (void)bar_blk_free, (void)bar_acc_full, (void)bar_acc_drained, (void)bar_epi, \
         (void)row, (void)bp;
 
-__global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) {
-    constexpr int NS = V3_ASLOTS;
+template<int K>
+__global__ void __maxnreg__(V3_REGS_LAUNCH<K>) search_mma3_kernel(const MmaArgs p) {
+    constexpr int KA = K / 4; // 128-bit atoms per descriptor
+    constexpr int NS = V3_ASLOTS<K>;
     constexpr int NP = V3_PACKED;
+    constexpr int PACKED_BYTES = V3_PACKED_BYTES<K>;
+    constexpr int BLK_BYTES = KA * ATOM_BYTES;
+    constexpr uint32_t A_COLS = 32u * KA; // TMEM columns of one A tile
+    constexpr int OFF = V3_OFFSET<K>;
     extern __shared__ uint8_t smem_raw[];
     // packed full [NP], packed free [NP], A full [NS], A free [NS], block full [2][2], block free [2][2],
     // accumulator full [3][2], drained [3][2] (per accumulator and block, see search_mma2_kernel), epilogue sync [2]
@@ -1344,7 +1379,7 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
     tc_fence_after();
 
     if (warp >= 12) {
-        regs_shrink<V3_REGS_ISSUER>();
+        regs_shrink<V3_REGS_ISSUER<K>>();
         V3_ROLE_CONTEXT
     if (warp == 15) {
         // idle: setmaxnreg works on warpgroups
@@ -1353,8 +1388,8 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
         {
             const int h = warp - 12;
             const uint32_t u_tmem = uniform(tmem);
-            const uint64_t desc_b0 = smem_desc(uniform(s_blk)) + (uint32_t)h * (uint32_t)(ATOM_BYTES >> 4);
-            constexpr uint32_t BUFFER_STEP = (2 * ATOM_BYTES) >> 4;
+            const uint64_t desc_b0 = smem_desc(uniform(s_blk)) + (uint32_t)h * (uint32_t)(BLK_BYTES >> 4);
+            constexpr uint32_t BUFFER_STEP = (2 * BLK_BYTES) >> 4;
             uint32_t s = 0, a_phase = 0;
             // MMA group q = 2 g + h: accumulator a = q % 3; its previous use was group q - 3 of the other block, whose
             // "drained" barrier completes phase ((q - 3) / 6) & 1: both carried incrementally (d6 = (q - 3) % 6)
@@ -1374,9 +1409,11 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
                     tc_fence_after();
                     if (elect_one()) {
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            tc_mma_i8_ts(u_tmem + a * TN, u_tmem + V3_A_COL0 + s * 32u + (uint32_t)(kk * 8), desc_b + (uint32_t)((kk * 32) >> 4),
-                                         IDESC3, kk != 0);
+                        for (int qa = 0; qa < KA; ++qa)
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                tc_mma_i8_ts(u_tmem + a * TN, u_tmem + V3_A_COL0 + s * A_COLS + (uint32_t)(qa * 32 + kk * 8),
+                                             desc_b + (uint32_t)((qa * ATOM_BYTES + kk * 32) >> 4), IDESC3, (qa | kk) != 0);
                         tc_commit(bar_acc_full + 8 * (2 * a + h));
                         tc_commit(bar_a_free + 8 * s); // counts 2: both blocks have read the tile
                     }
@@ -1404,13 +1441,13 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
             // entries find their slots free
             uint32_t slot = 0, free_phase = 1u;
             bool wrapped = false;
-            const uint32_t tail_bytes = (uint32_t)(cols - (ntiles - 1) * TN) * 16u; // the row's last (possibly short) tile
+            const uint32_t tail_bytes = (uint32_t)(cols - (ntiles - 1) * TN) * (uint32_t)(K * 4); // the row's last (possibly short) tile
             auto put = [&](const uint32_t* src, uint32_t bytes) -> bool {
                 if (wrapped)
                     if (!mbar_wait(bar_packed_free + 8 * slot, free_phase, &s_watch))
                         return false;
                 mbar_expect_tx(bar_packed_full + 8 * slot, bytes);
-                bulk_copy_g2s(s_packed + slot * (uint32_t)V3_PACKED_BYTES, src, bytes, bar_packed_full + 8 * slot);
+                bulk_copy_g2s(s_packed + slot * (uint32_t)PACKED_BYTES, src, bytes, bar_packed_full + 8 * slot);
                 if (++slot == (uint32_t)NP) {
                     slot = 0;
                     free_phase ^= 1u;
@@ -1424,13 +1461,13 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
                 for (int e = 0; e < 2; ++e) {
                     // a second block beyond the row: one copy of the row's last pixel, which the producers replicate
                     const int base = min((2 * bp + e) * TN, cols - 1);
-                    if (!put(rrow + (size_t)base * 4, (uint32_t)min(TN, cols - base) * 16u))
+                    if (!put(rrow + (size_t)base * K, (uint32_t)min(TN, cols - base) * (uint32_t)(K * 4)))
                         goto teardown;
                 }
                 for (int t = 0; t < ntiles - 1; ++t)
-                    if (!put(lrow + (size_t)t * (TN * 4), (uint32_t)V3_PACKED_BYTES))
+                    if (!put(lrow + (size_t)t * (TN * K), (uint32_t)PACKED_BYTES))
                         goto teardown;
-                if (!put(lrow + (size_t)(ntiles - 1) * (TN * 4), tail_bytes))
+                if (!put(lrow + (size_t)(ntiles - 1) * (TN * K), tail_bytes))
                     goto teardown;
                 if (++bp == npairs) {
                     bp = 0;
@@ -1442,26 +1479,32 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
     } else if (warp >= 8) {
         // ---- producers: ring entries 0, 1 of an item = the right blocks -> shared memory (signed), entries 2.. = left
         //      tiles -> tensor memory (unsigned). Thread r = row r of a block = TMEM lane r of a tile. ----
-        regs_shrink<V3_REGS_PRODUCER>();
+        regs_shrink<V3_REGS_PRODUCER<K>>();
         V3_ROLE_CONTEXT
         const int r = (int)pinned((uint32_t)(tid - 2 * TM));
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         // everything a ring entry needs is carried incrementally: packed slot + parity, A slot + parity
         uint32_t ps = 0, full_phase = 0, as = 0, a_free_phase = 1u;
         bool a_wrapped = false;
-        const uint32_t my_px = s_packed + (uint32_t)r * 16u; // this thread's pixel of a full tile, + slot * V3_PACKED_BYTES
-        const uint32_t my_tail_px = s_packed + (uint32_t)min(r, cols - (ntiles - 1) * TN - 1) * 16u; // of the row's last tile
+        const uint32_t my_px = s_packed + (uint32_t)r * (uint32_t)(K * 4); // this thread's pixel of a full tile, + slot * PACKED_BYTES
+        const uint32_t my_tail_px = s_packed + (uint32_t)min(r, cols - (ntiles - 1) * TN - 1) * (uint32_t)(K * 4); // of the row's last tile
         for (int n = 0; n < nitems; ++n) {
             for (int e = 0; e < 2; ++e) {
                 const int valid = min(TN, cols - min((2 * bp + e) * TN, cols - 1));
                 if (!mbar_wait(bar_packed_full + 8 * ps, full_phase, &s_watch))
                     goto teardown;
-                const uint4 d = ld_shared_v4(s_packed + ps * (uint32_t)V3_PACKED_BYTES + (uint32_t)min(r, valid - 1) * 16u);
+                uint4 d[KA];
+                {
+                    const uint32_t src = s_packed + ps * (uint32_t)PACKED_BYTES + (uint32_t)min(r, valid - 1) * (uint32_t)(K * 4);
+#pragma unroll
+                    for (int q = 0; q < KA; ++q)
+                        d[q] = ld_shared_v4(src + 16u * q);
+                }
                 const uint32_t b = 2u * ((uint32_t)n & 1u) + (uint32_t)e;
                 if (n >= 2) // the MMAs of the item that used this buffer are complete
                     if (!mbar_wait(bar_blk_free + 8 * b, (((uint32_t)n >> 1) - 1u) & 1u, &s_watch))
                         goto teardown;
-                expand_block_pixel(d, s_blk + b * ATOM_BYTES, r);
+                expand_block_pixel<K>(d, s_blk + b * BLK_BYTES, r);
                 mbar_arrive(bar_packed_free + 8 * ps); // after the stores that consumed the loaded registers
                 fence_async_smem();
                 mbar_arrive(bar_blk_full + 8 * b);
@@ -1473,12 +1516,18 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
             for (int t = 0; t < ntiles; ++t) {
                 if (!mbar_wait(bar_packed_full + 8 * ps, full_phase, &s_watch))
                     goto teardown;
-                const uint4 d = ld_shared_v4((t == ntiles - 1 ? my_tail_px : my_px) + ps * (uint32_t)V3_PACKED_BYTES);
+                uint4 d[KA];
+                {
+                    const uint32_t src = (t == ntiles - 1 ? my_tail_px : my_px) + ps * (uint32_t)PACKED_BYTES;
+#pragma unroll
+                    for (int q = 0; q < KA; ++q)
+                        d[q] = ld_shared_v4(src + 16u * q);
+                }
                 if (a_wrapped)
                     if (!mbar_wait(bar_a_free + 8 * as, a_free_phase, &s_watch))
                         goto teardown;
                 tc_fence_after();
-                expand_moving_to_tmem(d, lane_base + V3_A_COL0 + as * 32u);
+                expand_moving_to_tmem<K>(d, lane_base + V3_A_COL0 + as * A_COLS);
                 mbar_arrive(bar_packed_free + 8 * ps);
                 tc_fence_before();
                 mbar_arrive(bar_a_full + 8 * as);
@@ -1531,7 +1580,7 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
             const int col0 = (2 * bp + h) * TN; // first right pixel of my block (may lie beyond the row: nothing is stored then)
             const int fwd_cols = col0 < cols ? cols : 0; // left pixels whose forward key this block may lower
             for (int t = 0; t < ntiles; ++t) {
-                const uint32_t tile2 = (uint32_t)t * 0x00010001u;
+                const uint32_t tile2 = (uint32_t)(t + OFF) * 0x00010001u; // + the popcount byte's bias (256 bits): the running minima are >= 0
                 uint32_t f[8];
                 tc_load32_wait(lo);
                 tc_load64_packed_issue(lane_base + a * TN + 64u, hi);
@@ -1568,8 +1617,8 @@ __global__ void __maxnreg__(V3_REGS_LAUNCH) search_mma3_kernel(const MmaArgs p) 
                 for (int c = 0; c < 8; ++c)
                     f[c] = __vimin3_s16x2(f[c], (uint32_t)hi[16 + c], (uint32_t)hi[24 + c]);
                 const uint32_t m2 = __vimin3_s16x2(__vimin3_s16x2(f[0], f[1], f[2]), __vimin3_s16x2(f[3], f[4], f[5]), __vmins2(f[6], f[7]));
-                // both halves are non-negative: m = 128 ham + column; key = ham << 16 | col0 + column = 512 m - 511 (m & 127) + col0
-                const uint32_t m = min(m2 & 0xFFFFu, m2 >> 16);
+                // m = 128 ham + column (>= 0 once the bias is added back); key = ham << 16 | col0 + column = 512 m - 511 (m & 127) + col0
+                const uint32_t m = OFF ? (uint32_t)(min((int)(short)(m2 & 0xFFFFu), (int)(short)(m2 >> 16)) + OFF) : min(m2 & 0xFFFFu, m2 >> 16);
                 const int i = t * TM + lane128;
                 if (i < fwd_cols)
                     atomicMin(p.fwd_first + row_at + i, m * 512u + (uint32_t)col0 - (m & 127u) * 511u);
@@ -1708,9 +1757,11 @@ cudaError_t launch_k(MmaArgs p, int dirs, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+template<int K>
 cudaError_t launch_k3(MmaArgs p, cudaStream_t stream) {
-    auto kernel = search_mma3_kernel;
-    cudaError_t err = configure_once(kernel, V3_SMEM_BYTES);
+    auto kernel = search_mma3_kernel<K>;
+    constexpr int smem = V3_SMEM_BYTES<K>;
+    cudaError_t err = configure_once(kernel, smem);
     if (err != cudaSuccess)
         return err;
     p.mtiles = (p.cols + 2 * TN - 1) / (2 * TN); // pairs of right blocks per row
@@ -1722,7 +1773,7 @@ cudaError_t launch_k3(MmaArgs p, cudaStream_t stream) {
         return err;
     const int sms = sm_count_of_current_device();
     const unsigned grid = (unsigned)(p.items < sms ? p.items : sms);
-    kernel<<<grid, V3_THREADS, V3_SMEM_BYTES, stream>>>(p);
+    kernel<<<grid, V3_THREADS, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -1828,8 +1879,8 @@ void set_search_mma_colterm(bool on) {
 // Whether launch_search_mma takes the one-pass consistency kernel (search_mma3_kernel) for this search
 bool search_mma_onepass_applies(int K, int cols, int flags, int free_top_bits) {
     const int variant = search_mma_variant();
-    return K == 4 && cols >= 1 && cols <= COL_MAX + 1 && flags == FLAG_CONSISTENCY && free_top_bits >= 2 && (variant == 3 || variant == 0)
-        && search_mma_colterm();
+    return (K == 4 || K == 8) && cols >= 1 && cols <= COL_MAX + 1 && flags == FLAG_CONSISTENCY && free_top_bits >= 2
+        && (variant == 3 || variant == 0) && search_mma_colterm();
 }
 
 bool search_mma_supports(int K, int cols) {
@@ -1874,10 +1925,10 @@ cudaError_t launch_search_mma(
     const bool nodupes = (flags & FLAG_NODUPES) != 0;
     const long long pair_items = (long long)dirs * rows * ((cols + 2 * TM - 1) / (2 * TM));
     const int variant = search_mma_variant();
-    // one product for both directions: 128-bit descriptors whose top TWO bits are free, Consistency without no_dupes
+    // one product for both directions: 128- / 256-bit descriptors whose top TWO bits are free, Consistency without no_dupes
     if (search_mma_onepass_applies(K, cols, flags, free_top_bits)) {
-        note_search_kernel("mma3<K=4,nodupes=0,ct=2,onepass=1>");
-        return launch_k3(p, stream);
+        note_search_kernel("mma3<K=%d,nodupes=0,ct=2,onepass=1>", K);
+        return K == 4 ? launch_k3<4>(p, stream) : launch_k3<8>(p, stream);
     }
     const bool v2 = (K == 4 || K == 8) && (variant == 2 || (variant == 0 && pair_items >= 2 * sm_count_of_current_device()));
     // column term through the MMA (see fold32): only where the caller vouches for the free top bit

@@ -196,7 +196,9 @@ BENCHED = [
      "mma2<K=4,nodupes=1,ct=1,dirs=2>"),
     (64, np.uint8, 160, 512, dict(nxcorr_threshold=0.9, min_variance=2.0), "mma2<K=8,nodupes=1,ct=1,dirs=1>"),  # C4: 256 bits
     (64, np.uint8, 100, 700, dict(nxcorr_threshold=0.9, subpixel_step=0.2, consistency=True, max_lr_diff=1),
-     "mma2<K=8,nodupes=0,ct=1,dirs=2>"),
+     "mma3<K=8,nodupes=0,ct=2,onepass=1>"),  # 256 bits through the one-pass kernel (popcount byte with its bias)
+    (16, np.uint16, 120, 600, dict(nxcorr_threshold=0.9, mode_full=True, consistency=True, max_lr_diff=1),
+     "mma3<K=8,nodupes=0,ct=2,onepass=1>"),  # FULL, u16, 227 of 256 bits
     (16, np.uint16, 160, 512, dict(nxcorr_threshold=0.9, mode_full=True, consistency=True, max_lr_diff=1, no_dupes=True),
      "mma2<K=8,nodupes=1,ct=1,dirs=2>"),  # C3: FULL, u16
 ]
@@ -372,7 +374,7 @@ def test_search_engines_identical(handle, oracles, k, rows, cols, flags, top_bit
             assert kernel.startswith("popc<" if name == "popc" else "mma"), kernel
     finally:
         lb.set_search_engine("auto")
-    onepass = top_bit_free == 2 and k == 4 and flags == FLAG_CONSISTENCY
+    onepass = top_bit_free == 2 and k in (4, 8) and flags == FLAG_CONSISTENCY
     assert f"ct={2 if onepass else int(bool(top_bit_free) and k in (4, 8))}" in kernel, kernel
     if onepass:
         assert kernel.startswith("mma3<"), kernel

@@ -227,3 +227,29 @@ def test_onepass_folds_give_both_first_minima(cols):
     best_f, best_r = ham.min(axis=1), ham.min(axis=0)
     assert np.array_equal(fwd, (best_f << 16) | (ham == best_f[:, None]).argmax(axis=1))
     assert np.array_equal(rev, (best_r << 16) | (ham == best_r[None, :]).argmax(axis=0))
+
+
+def test_onepass_accumulator_256_bits_carries_the_popcount_with_a_bias():
+    """256-bit descriptors: popc(right) reaches 254 and no longer fits the signed operand byte, so the byte carries
+    popc - 128 and the accumulator is 128 ham + column - 16384: still a signed half word; adding 16384 + tile in the
+    reverse fold keeps the running minima in [0, 32767]."""
+    rng = np.random.default_rng(8)
+    left = rng.integers(0, 2**32, size=(128, 8), dtype=np.uint64).astype(np.uint32)
+    right = rng.integers(0, 2**32, size=(TN, 8), dtype=np.uint64).astype(np.uint32)
+    left[:, -1] &= 0x3FFFFFFF
+    right[:, -1] &= 0x3FFFFFFF
+    left[0], right[0] = 0, 0
+    left[1, :7], right[1, :7] = 0xFFFFFFFF, 0xFFFFFFFF
+    left[1, 7], right[2, 7] = 0x3FFFFFFF, 0x3FFFFFFF  # 254 set bits on one side, none on the other: ham = 254
+    right[2, :7] = 0xFFFFFFFF
+    a, b = operands(left, False), operands(right, True)
+    pos6, pos7 = 32 * 8 - 5, 32 * 8 - 1
+    a[:, pos6], a[:, pos7] = 128, 1
+    b[:, pos6], b[:, pos7] = popcount(right) - 128, np.arange(TN)
+    assert b.min() >= -128 and b.max() <= 127
+    acc = a @ b.T
+    ham = popcount(left[:, None, :] ^ right[None, :, :])
+    assert ham.max() == 254
+    assert np.array_equal(acc, 128 * ham + np.arange(TN)[None, :] - 16384)
+    assert acc.min() >= -(2**15) and acc.max() < 2**15
+    assert (acc + 16384 + 63).max() < 2**15 and (acc + 16384).min() >= 0  # + tile index (rows of up to 8192 pixels)
