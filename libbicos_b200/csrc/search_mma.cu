@@ -41,7 +41,7 @@
 // Three kernels: search_mma_kernel (every width; 2 CTAs per SM up to 256 bits; 128 left pixels per item,
 // both operands in shared memory, 2 accumulators), search_mma2_kernel (128 / 256 bits, large images;
 // 1 CTA per SM, 256 left pixels per item, left operand resident in TMEM, 3 accumulators in rotation,
-// one issuer per half) and search_mma3_kernel (128 bits, Consistency without no_dupes: ONE product per
+// one issuer per half) and search_mma3_kernel (128 / 256 bits, Consistency without no_dupes: ONE product per
 // row, the forward minima folded in-thread and the reverse minima elementwise across the row's tiles,
 // see its own header below). DESIGN.md 3.2a / 3.2b have the measurements that led from one to the next.
 
@@ -1130,7 +1130,7 @@ teardown:
 }
 
 // ---------------------------------------------------------------------------------------------------
-// One-pass consistency search (128-bit descriptors, Consistency without no_dupes: the metric configuration).
+// One-pass consistency search (128- and 256-bit descriptors, Consistency without no_dupes: the metric configuration).
 // The two kernels above compute the W x W Hamming matrix of a row twice, once per direction, because a
 // minimum ACROSS the TMEM lanes of one accumulator costs a cross-lane reduction per column. Here every pair
 // is computed once (SURVEY 8d's count) and both minima are taken from the same accumulator:
@@ -1841,7 +1841,7 @@ unsigned int search_mma_take_timeout() {
 }
 
 // 1 = two CTAs per SM, both operands in shared memory; 2 = one CTA per SM, left operand in tensor memory
-// (128 / 256 bits); 3 = the one-pass consistency kernel (128 bits, Consistency without no_dupes, two free top bits);
+// (128 / 256 bits); 3 = the one-pass consistency kernel (128 / 256 bits, Consistency without no_dupes, two free top bits);
 // 0 = automatic: 3 where it applies, else 2 where it applies and the image has an item for every SM (measured on
 // the B200: 1.25 against 1.34 ms on the metric configuration, 2.35 against 2.63 ms for 256 bits x 4096
 // columns; small images are served better by the finer items of variant 1). Environment
